@@ -1,0 +1,152 @@
+/*
+ * dfk_b200.h -- C ABI of the B200-native DFMI readout hot path.
+ *
+ * This is the drop-in boundary for mdovale/DeepFMKit's readout path: every
+ * entry point names the reference interface it replaces (file:line into the
+ * upstream repo).  Plain pointers and sizes only; all floating point is IEEE
+ * fp64, little endian, row-major.  The library is CUDA-only: there is no CPU
+ * fallback, and every call fails with DFK_ERR_CUDA if no sm_100 device is
+ * usable.
+ *
+ * Conventions
+ *   - harmonic vector  qi[b] = [Q_1..Q_N, I_1..I_N]   (Q = cosine mean, I = sine mean, 1/R
+ *     normalised) -- the layout of QI_data_mean in fitters.py:45-49
+ *   - parameter vector [amp, m, phi, psi]              -- fit.py:93
+ *   - result row       [amp, m, phi, psi, dc, ssq, fitok, aux] (8 doubles, DFK_ROW_STRIDE);
+ *     columns 0..6 are the reference's result-frame columns (fitters.py:55-58), fitok stored
+ *     as a double holding 0/1/2; aux = accepted LM steps (NLS) or 0 (EKF)
+ *   - "dev" pointers are device pointers on the context's device; "host" pointers are host
+ *     memory (pinned memory is detected and copied from directly, pageable memory is staged)
+ *   - all calls return 0 on success or a negative DFK_ERR_* code; dfk_last_error() gives the
+ *     message for the calling thread.  Numerical failure of a fit is never an error: it is
+ *     reported through fitok exactly as the reference does (fit.py:334-349).
+ */
+#ifndef DFK_B200_H
+#define DFK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFK_ABI_VERSION 1
+#define DFK_ROW_STRIDE 8
+#define DFK_MAX_HARMONICS 64
+
+#define DFK_OK 0
+#define DFK_ERR_ARG (-1)
+#define DFK_ERR_CUDA (-2)
+#define DFK_ERR_NOMEM (-3)
+
+/* Tunables of the reference solver; module globals in fit.py:5-16 that users patch at run
+ * time, so the host shim reads them at call time and passes them here. */
+typedef struct dfk_lm_opts {
+    int32_t max_lma_steps;        /* fit.py:7   MAX_LMA_STEPS               (100)  */
+    int32_t lanes_per_fit;        /* 0 = auto; 1,2,4,8,16,32 lanes cooperate on one fit */
+    double conv_improve;          /* fit.py:8   LMA_CONVERGENCE_IMPROVE      (1e-9) */
+    double conv_param;            /* fit.py:9   LMA_CONVERGENCE_PARAM_CHANGE (1e-9) */
+    double fitok_threshold;       /* fit.py:10  FITOK_THRESHOLD              (1e-3) */
+    double m_grid_min;            /* fit.py:12  M_GRID_MIN                   (5.0)  */
+    double m_grid_max;            /* fit.py:13  M_GRID_MAX                   (30.0) */
+    double m_grid_step;           /* fit.py:14  M_GRID_STEP                  (0.5)  */
+    double bessel_amp_threshold;  /* fit.py:15  BESSEL_AMP_THRESHOLD         (0.05) */
+    double sincos_amp_threshold;  /* fit.py:16  SINCOS_AMP_THRESHOLD         (0.1)  */
+} dfk_lm_opts;
+
+/* EKF settings; defaults of EKFFitter.fit (fitters.py:241-248). */
+typedef struct dfk_ekf_opts {
+    double init[4];     /* init_a, init_m, init_phi, init_psi   (1.6, 6.0, 0, 0) */
+    double p0_diag[5];  /* initial covariance diagonal           (1,1,1,1,1)      */
+    double q_diag[5];   /* process noise diagonal (1e-8,1e-8,1e-6,1e-6,1e-8)      */
+    double r_val;       /* measurement variance; NaN = var(record) per channel (fitters.py:256) */
+} dfk_ekf_opts;
+
+/* Work counters of the LM kernels (for the FP64 flop accounting in bench.py). */
+typedef struct dfk_lm_counters {
+    uint64_t n_state;   /* model+Jacobian evaluations  (fit.py:68  coeffs)  */
+    uint64_t n_ssq;     /* residual-only evaluations   (fit.py:152 ssqf)    */
+    uint64_t n_solve;   /* damped 4x4 solves           (fit.py:169 msolve)  */
+    uint64_t n_grid;    /* grid-search fallbacks       (fit.py:260)         */
+    uint64_t n_bessel_steps; /* Miller recurrence steps over all evaluations */
+} dfk_lm_counters;
+
+typedef struct dfk_ctx dfk_ctx;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int dfk_abi_version(void);
+const char* dfk_last_error(void);
+int dfk_device_count(void);
+/* One context per (thread, device): owns two streams, pinned staging and device scratch. */
+int dfk_create(int device, dfk_ctx** out);
+int dfk_destroy(dfk_ctx* ctx);
+/* Use a caller-owned stream (e.g. torch's current stream) for the device-pointer calls;
+ * NULL restores the context's own stream. */
+int dfk_set_stream(dfk_ctx* ctx, void* cuda_stream);
+int dfk_synchronize(dfk_ctx* ctx);
+void dfk_default_lm_opts(dfk_lm_opts* o);
+void dfk_default_ekf_opts(dfk_ekf_opts* o);
+
+/* ---- device-pointer kernels --------------------------------------------------------------- */
+/* Harmonic lock-in of nbuf contiguous buffers of R samples.
+ * Replaces calculate_quadratures (fit.py:18-66) and the three mean() loops
+ * (fitters.py:45-49, 380-384, 436-440) plus dc = mean(buffer) (fitters.py:57).
+ * w0 is rad/sample exactly as the reference passes it (fitters.py:39).
+ * qi_dev: nbuf x 2N, dc_dev: nbuf. */
+int dfk_demod(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
+              double* qi_dev, double* dc_dev);
+
+/* Batched LM fit of (amp, m, phi, psi) on nbuf harmonic vectors.
+ * Replaces fit.fit (fit.py:322-362) incl. coeffs/ssqf/msolve/_run_lma_fit/_find_best_initial_guess.
+ * guess_dev: 4 doubles when guess_stride == 0 (one seed for all fits, fitters.py:404-417) or
+ * nbuf x guess_stride.  dc_dev may be NULL.  rows_dev: nbuf x DFK_ROW_STRIDE. */
+int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, const double* guess_dev,
+               int64_t guess_stride, const double* dc_dev, const dfk_lm_opts* opts, double* rows_dev);
+
+/* Whole NLS readout of one device-resident record: demod, fit buffer 0 from init, fit buffers
+ * 1.. seeded from buffer 0's result.  Replaces StandardNLSFitter._fit_parallel and its
+ * multiprocessing.Pool (fitters.py:395-428) at n_cores >= nbuf.  seeded == 0 fits every buffer
+ * from init (independent single-buffer fits, workers.py:167-173). */
+int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
+                    const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
+
+/* 5-state EKF over C independent channels, one thread per channel.
+ * Replaces EKFFitter.fit (fitters.py:214-320).  Sample (t, c) is z_dev[t*ld_t + c*ld_c]
+ * (time-major: ld_t = C, ld_c = 1; channel-major: ld_t = 1, ld_c = T).
+ * rows_dev: C x nbuf x DFK_ROW_STRIDE with nbuf = T / R. */
+int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c,
+                int64_t R, double f_samp, double f_mod, const dfk_ekf_opts* opts, double* rows_dev);
+
+/* 'snr'-mode synthetic record (physics.py:475-530) generated on the device with a counter-based
+ * RNG: y = A(1 + C cos(phi0 + m cos(2 pi f_mod t + psi0))) + sigma N(0,1), sigma from snr_db.
+ * Statistically (not bitwise) equivalent to the reference's MT19937 stream.  C channels,
+ * channel-major [C][T]; channel c uses phi0 + c*dphi and seed + c. */
+int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double f_samp, double f_mod,
+                      double m, double amp, double visibility, double phi0, double dphi, double psi0,
+                      double snr_db, uint64_t seed);
+
+/* ---- host-pointer entry points (what the reference-side shim binds) ---------------------- */
+/* StandardNLSFitter.fit on one host record (fitters.py:330-428): nsamp samples, buffers of R,
+ * slabs streamed host->device on a copy stream while the previous slab is demodulated and
+ * fitted.  rows_host: (nsamp / R) x DFK_ROW_STRIDE. */
+int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                     const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_host);
+
+/* EKFFitter.fit on host records, channel-major [C][T]. rows_host: C x (T/R) x DFK_ROW_STRIDE. */
+int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64_t R, double f_samp,
+                 double f_mod, const dfk_ekf_opts* opts, double* rows_host);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* Counters accumulated by the LM kernels since the last reset (device -> host copy, syncs). */
+int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset);
+/* Kernel launches issued through this context since creation (bench.py's gpu_launches). */
+int64_t dfk_launch_count(dfk_ctx* ctx);
+/* Which demod kernel the given geometry selects: 1 = folded TMA kernel, 0 = general kernel. */
+int dfk_demod_path(int64_t R, double w0);
+/* Bessel J_0..J_nmax(x) by the device's Miller recurrence, evaluated on the device (testing). */
+int dfk_bessel_dev(dfk_ctx* ctx, const double* x_dev, int64_t n, int32_t nmax, double* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFK_B200_H */
