@@ -1,0 +1,257 @@
+"""ctypes binding of libdfk_b200.so (the C ABI in include/dfk_b200.h).
+
+There is no CPU implementation behind this module: if the library is missing or no B200 is
+visible, every call raises.  PyTorch is used by callers only for device memory and streams;
+the library itself takes raw device/host pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+from ._build import LIB_PATH
+
+ROW_STRIDE = 8
+MAX_HARMONICS = 64
+ROW_COLUMNS = ("amp", "m", "phi", "psi", "dc", "ssq", "fitok")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class LmOpts(ctypes.Structure):
+    _fields_ = [("max_lma_steps", ctypes.c_int32), ("lanes_per_fit", ctypes.c_int32),
+                ("conv_improve", ctypes.c_double), ("conv_param", ctypes.c_double),
+                ("fitok_threshold", ctypes.c_double), ("m_grid_min", ctypes.c_double),
+                ("m_grid_max", ctypes.c_double), ("m_grid_step", ctypes.c_double),
+                ("bessel_amp_threshold", ctypes.c_double), ("sincos_amp_threshold", ctypes.c_double)]
+
+
+class EkfOpts(ctypes.Structure):
+    _fields_ = [("init", ctypes.c_double * 4), ("p0_diag", ctypes.c_double * 5),
+                ("q_diag", ctypes.c_double * 5), ("r_val", ctypes.c_double)]
+
+
+class LmCounters(ctypes.Structure):
+    _fields_ = [("n_state", ctypes.c_uint64), ("n_ssq", ctypes.c_uint64), ("n_solve", ctypes.c_uint64),
+                ("n_grid", ctypes.c_uint64), ("n_bessel_steps", ctypes.c_uint64)]
+
+
+# every symbol include/dfk_b200.h declares: name -> (restype, argtypes)
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_d = ctypes.c_double
+SYMBOLS = {
+    "dfk_abi_version": (ctypes.c_int, []),
+    "dfk_last_error": (ctypes.c_char_p, []),
+    "dfk_device_count": (ctypes.c_int, []),
+    "dfk_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_vp)]),
+    "dfk_destroy": (ctypes.c_int, [_vp]),
+    "dfk_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "dfk_use_legacy_default_stream": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dfk_synchronize": (ctypes.c_int, [_vp]),
+    "dfk_default_lm_opts": (None, [ctypes.POINTER(LmOpts)]),
+    "dfk_default_ekf_opts": (None, [ctypes.POINTER(EkfOpts)]),
+    "dfk_demod": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
+    "dfk_lm_fit": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_nls_fit_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_nls_fit_batch_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
+                                             ctypes.POINTER(LmOpts), _vp]),
+    "dfk_ekf_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
+    "dfk_synth_snr_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d, ctypes.c_uint64]),
+    "dfk_nls_fit_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
+    "dfk_lm_counters_read": (ctypes.c_int, [_vp, ctypes.POINTER(LmCounters), _i32]),
+    "dfk_profile_enable": (ctypes.c_int, [_vp, _i32]),
+    "dfk_profile_read": (ctypes.c_int, [_vp, c_double_p, ctypes.POINTER(_i64), _i32]),
+    "dfk_launch_count": (_i64, [_vp]),
+    "dfk_demod_path": (ctypes.c_int, [_i64, _d]),
+    "dfk_bessel_dev": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen the in-tree library and type every entry point. Raises if it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(deepfmkit_b200 has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.dfk_abi_version() != 1:
+            raise RuntimeError("libdfk_b200.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise RuntimeError(f"dfk_b200 error {rc}: {lib.dfk_last_error().decode(errors='replace')}")
+
+
+def default_lm_opts() -> LmOpts:
+    o = LmOpts()
+    load_library().dfk_default_lm_opts(ctypes.byref(o))
+    return o
+
+
+def default_ekf_opts() -> EkfOpts:
+    o = EkfOpts()
+    load_library().dfk_default_ekf_opts(ctypes.byref(o))
+    return o
+
+
+def _host_array(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data
+
+
+class Context:
+    """One dfk_ctx: a device, its streams and scratch. Not shared between threads."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self._h = _vp()
+        _check(self.lib, self.lib.dfk_create(int(device), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.dfk_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- streams ----------------------------------------------------------------------------------
+    def use_torch_stream(self, stream=None):
+        """Issue device-pointer calls on a torch stream (default: torch's current stream)."""
+        import torch
+        stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        handle = int(stream.cuda_stream)
+        if handle == 0:
+            _check(self.lib, self.lib.dfk_use_legacy_default_stream(self._h, 1))
+        else:
+            _check(self.lib, self.lib.dfk_set_stream(self._h, _vp(handle)))
+
+    def use_own_stream(self):
+        _check(self.lib, self.lib.dfk_set_stream(self._h, None))
+
+    def synchronize(self):
+        _check(self.lib, self.lib.dfk_synchronize(self._h))
+
+    # ---- device-pointer calls (pointers are ints, e.g. tensor.data_ptr()) -----------------------------
+    def demod(self, x_ptr, nbuf, R, N, w0, qi_ptr, dc_ptr):
+        _check(self.lib, self.lib.dfk_demod(self._h, x_ptr, nbuf, R, N, w0, qi_ptr, dc_ptr))
+
+    def lm_fit(self, qi_ptr, nbuf, N, guess_ptr, guess_stride, dc_ptr, opts, rows_ptr):
+        _check(self.lib, self.lib.dfk_lm_fit(self._h, qi_ptr, nbuf, N, guess_ptr, guess_stride, dc_ptr,
+                                             ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def nls_fit_dev(self, x_ptr, nbuf, R, N, w0, init, seeded, opts, rows_ptr):
+        init_arr = (ctypes.c_double * 4)(*[float(v) for v in init])
+        _check(self.lib, self.lib.dfk_nls_fit_dev(self._h, x_ptr, nbuf, R, N, w0, init_arr, int(bool(seeded)),
+                                                  ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def nls_fit_batch_dev(self, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init, init_dev_ptr, init_stride, seeded,
+                          opts, rows_ptr):
+        init_arr = (ctypes.c_double * 4)(*[float(v) for v in init]) if init is not None else None
+        _check(self.lib, self.lib.dfk_nls_fit_batch_dev(self._h, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init_arr,
+                                                        init_dev_ptr, init_stride, int(bool(seeded)),
+                                                        ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def ekf_dev(self, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, rows_ptr):
+        _check(self.lib, self.lib.dfk_ekf_dev(self._h, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod,
+                                              ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def synth_snr_dev(self, x_ptr, T, C, f_samp, f_mod, m, amp=1.0, visibility=1.0, phi0=0.0, dphi=0.0, psi0=0.0,
+                      snr_db=40.0, seed=0):
+        _check(self.lib, self.lib.dfk_synth_snr_dev(self._h, x_ptr, T, C, f_samp, f_mod, m, amp, visibility, phi0,
+                                                    dphi, psi0, snr_db, int(seed)))
+
+    def bessel_dev(self, x_ptr, n, nmax, out_ptr):
+        _check(self.lib, self.lib.dfk_bessel_dev(self._h, x_ptr, n, nmax, out_ptr))
+
+    # ---- host-pointer calls ----------------------------------------------------------------------------
+    def nls_fit_host(self, x, R, N, w0, init, seeded=True, opts=None, rows_out=None):
+        """x: 1-D float64 host array (numpy or a pinned torch tensor's numpy view). Returns rows[nbuf, 8]."""
+        x, xp = _host_array(x)
+        nbuf = x.size // int(R)
+        rows = rows_out if rows_out is not None else np.empty((nbuf, ROW_STRIDE), dtype=np.float64)
+        init_arr = (ctypes.c_double * 4)(*[float(v) for v in init])
+        _check(self.lib, self.lib.dfk_nls_fit_host(self._h, xp, x.size, int(R), int(N), float(w0), init_arr,
+                                                   int(bool(seeded)), ctypes.byref(opts) if opts is not None else None,
+                                                   rows.ctypes.data))
+        return rows
+
+    def ekf_host(self, z, R, f_samp, f_mod, opts=None):
+        """z: [C, T] float64 host array (channel-major). Returns rows[C, nbuf, 8]."""
+        z, zp = _host_array(np.atleast_2d(z))
+        C, T = z.shape
+        nbuf = T // int(R)
+        rows = np.empty((C, nbuf, ROW_STRIDE), dtype=np.float64)
+        _check(self.lib, self.lib.dfk_ekf_host(self._h, zp, T, C, int(R), float(f_samp), float(f_mod),
+                                               ctypes.byref(opts) if opts is not None else None, rows.ctypes.data))
+        return rows
+
+    # ---- introspection ---------------------------------------------------------------------------------
+    def lm_counters(self, reset=False) -> dict:
+        c = LmCounters()
+        _check(self.lib, self.lib.dfk_lm_counters_read(self._h, ctypes.byref(c), int(bool(reset))))
+        return {k: int(getattr(c, k)) for k, _ in LmCounters._fields_}
+
+    def profile_enable(self, on=True):
+        _check(self.lib, self.lib.dfk_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self, reset=False) -> dict:
+        """Summed device milliseconds and region counts: demod launches and LM launches."""
+        ms = (ctypes.c_double * 2)()
+        n = (_i64 * 2)()
+        _check(self.lib, self.lib.dfk_profile_read(self._h, ms, n, int(bool(reset))))
+        return {"demod_ms": ms[0], "demod_regions": int(n[0]), "lm_ms": ms[1], "lm_regions": int(n[1])}
+
+    def launch_count(self) -> int:
+        return int(self.lib.dfk_launch_count(self._h))
+
+
+def demod_path(R, w0) -> int:
+    return int(load_library().dfk_demod_path(int(R), float(w0)))
+
+
+def device_count() -> int:
+    return int(load_library().dfk_device_count())
+
+
+_ctx_cache = threading.local()
+
+
+def get_context(device: int = 0) -> Context:
+    """Per-thread, per-device cached context."""
+    cache = getattr(_ctx_cache, "ctx", None)
+    if cache is None:
+        cache = _ctx_cache.ctx = {}
+    if device not in cache:
+        cache[device] = Context(device)
+    return cache[device]

@@ -1,0 +1,109 @@
+"""The façade call of the reference, ``DeepFitFramework.fit`` (core.py:424-517), over the GPU fitters.
+
+Only the fitting entry point and the two containers it touches are provided: simulation, file I/O,
+plotting and the experimental W-DFMI fitters stay with the reference (INTEGRATION.md shows how the
+reference's own ``DeepFitFramework`` is pointed at these fitters instead).  The call signature, the
+default ``fit_label``, the ``tau`` column, the error behaviour (log + ``None``) and the scalar fields
+of the returned fit object are those of the reference.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .fitters import EKFFitter, StandardNLSFitter
+
+
+class DeepRawObject:
+    """One channel of raw data: what the fitters read (data.py:16-118 holds the full container)."""
+
+    def __init__(self, data=None, f_samp=None, f_mod=None, label=None, sim=None, t0=0):
+        import pandas as pd
+        if data is not None and not hasattr(data, "columns"):
+            data = pd.DataFrame(np.asarray(data, dtype=np.float64).reshape(-1), columns=["ch0"])
+        self.data = data
+        self.f_samp = f_samp
+        self.f_mod = f_mod
+        self.label = label
+        self.sim = sim
+        self.t0 = t0
+        self.phi_sim = None
+
+
+class DeepFitObject:
+    """Result arrays + fit geometry, the fields core.py:372-386 fills."""
+
+    def __init__(self):
+        self.label = None
+        self.n = self.R = self.fs = self.nbuf = None
+        self.ndata = self.init_a = self.init_m = 0
+        self.t0 = 0
+        self.f_samp = self.f_mod = None
+        self.ssq = self.amp = self.m = self.tau = self.phi = self.psi = self.dc = self.time = None
+
+
+class DeepFitFramework:
+    def __init__(self):
+        self.sims = {}
+        self.raws = {}
+        self.fits = {}
+        self.fits_df = {}
+
+    def load_raw_object(self, raw: DeepRawObject, label=None):
+        label = label or raw.label
+        raw.label = label
+        self.raws[label] = raw
+        return raw
+
+    def fit_init(self, label, n):
+        """(R, fs, nbuf) of a fitting run (core.py:390-422)."""
+        raw = self.raws[label]
+        R = int(raw.f_samp / raw.f_mod * n)
+        fs = raw.f_samp / R
+        nbuf = int(raw.data.shape[0] / R)
+        if nbuf == 0:
+            logging.error("Check buffer size !! Calculated nbuf is zero.")
+        return R, fs, nbuf
+
+    def fit(self, main_label, method="nls", fit_label=None, **kwargs):
+        fitter_map = {"nls": StandardNLSFitter, "ekf": EKFFitter}
+        if method not in fitter_map:
+            logging.error(f"Unknown fit method: '{method}'. Available: {list(fitter_map.keys())}")
+            return
+        FitterClass = fitter_map[method]
+        if main_label not in self.raws:
+            logging.error(f"Invalid raw data label: '{main_label}' !!")
+            return
+        main_raw = self.raws[main_label]
+        if fit_label is None:
+            fit_label = f"{main_label}_{method}"
+        n_cycles = kwargs.get("n")
+        if n_cycles is None:
+            sim = getattr(main_raw, "sim", None)
+            sim_obj = self.sims.get(sim.label if sim else main_label)
+            n_cycles = sim_obj.fit_n if sim_obj else 20
+        R, fs, nbuf = self.fit_init(main_label, n_cycles)
+
+        fit_config = {"n": n_cycles}
+        fitter = FitterClass(fit_config)
+        results_df = fitter.fit(main_raw=main_raw, **kwargs)
+        if results_df is None or results_df.empty:
+            logging.error(f"{FitterClass.__name__} returned no results.")
+            return None
+        sim = getattr(main_raw, "sim", None)
+        results_df["tau"] = results_df["m"] / (2 * np.pi * sim.laser.df) if sim else 0.0  # core.py:506-507
+        self.fits_df[fit_label] = results_df
+
+        fit = DeepFitObject()
+        fit.n, fit.R, fit.fs, fit.nbuf = n_cycles, R, fs, nbuf
+        fit.ndata, fit.init_a, fit.init_m = fit_config.get("ndata", 0), 0, 0  # Q5: the reference stores zeros
+        fit.t0 = getattr(main_raw, "t0", 0)
+        fit.f_samp, fit.f_mod = main_raw.f_samp, main_raw.f_mod
+        for col in ("ssq", "amp", "m", "tau", "phi", "psi", "dc"):
+            setattr(fit, col, np.asarray(results_df[col], dtype=np.float64) if col != "tau" or sim
+                    else np.zeros(len(results_df)))
+        fit.time = np.arange(0, fit.ssq.shape[0] / fit.fs, 1.0 / fit.fs)
+        fit.label = fit_label
+        self.fits[fit_label] = fit
+        return fit

@@ -1,0 +1,738 @@
+// C ABI of the B200-native DFMI readout path (declared in include/dfk_b200.h).
+// CUDA only: every entry point fails with DFK_ERR_CUDA when no usable device exists.
+#include "../../include/dfk_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "dfk_demod.cuh"
+#include "dfk_ekf_kernels.cuh"
+#include "dfk_lm_kernels.cuh"
+#include "dfk_synth.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DFK_CUDA(call)                                                                              \
+    do {                                                                                            \
+        const cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(DFK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct dfk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int smem_per_sm = 0;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, user_stream = nullptr;
+    bool use_user = false;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc;
+    int64_t launches = 0;
+    // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the
+    // demod launch [0] and around the LM launches [1], summed on read
+    bool profiling = false;
+    static constexpr int kProfSlots = 512;
+    cudaEvent_t prof_ev[2][kProfSlots][2] = {};
+    int prof_used[2] = {0, 0};
+    double prof_ms[2] = {0.0, 0.0};
+    int64_t prof_n[2] = {0, 0};
+    cudaStream_t stream() const { return use_user ? user_stream : own_stream; }
+};
+
+namespace {
+
+int ensure(dfk_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return DFK_OK;
+    if (b.ptr) {
+        // scratch may still be in use by kernels queued on the stream
+        DFK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        DFK_CUDA(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    const size_t want = std::max(bytes, static_cast<size_t>(256));
+    const cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        b.ptr = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? DFK_ERR_NOMEM : DFK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want,
+                    cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return DFK_OK;
+}
+
+int prof_drain(dfk_ctx* ctx) {  // fold recorded event pairs into the totals (synchronises)
+    for (int k = 0; k < 2; ++k) {
+        for (int i = 0; i < ctx->prof_used[k]; ++i) {
+            DFK_CUDA(cudaEventSynchronize(ctx->prof_ev[k][i][1]));
+            float ms = 0.f;
+            DFK_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[k][i][0], ctx->prof_ev[k][i][1]));
+            ctx->prof_ms[k] += ms;
+            ctx->prof_n[k]++;
+        }
+        ctx->prof_used[k] = 0;
+    }
+    return DFK_OK;
+}
+
+struct ProfScope {  // records an event pair around the launches issued while it lives
+    dfk_ctx* ctx;
+    int kind, slot;
+    cudaStream_t st;
+    ProfScope(dfk_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), slot(-1), st(s) {
+        if (!ctx->profiling) return;
+        if (ctx->prof_used[kind] == dfk_ctx::kProfSlots && prof_drain(ctx) != DFK_OK) return;
+        slot = ctx->prof_used[kind];
+        for (int e = 0; e < 2; ++e)
+            if (!ctx->prof_ev[kind][slot][e] && cudaEventCreate(&ctx->prof_ev[kind][slot][e]) != cudaSuccess) {
+                slot = -1;
+                return;
+            }
+        cudaEventRecord(ctx->prof_ev[kind][slot][0], st);
+    }
+    ~ProfScope() {
+        if (slot < 0) return;
+        cudaEventRecord(ctx->prof_ev[kind][slot][1], st);
+        ctx->prof_used[kind] = slot + 1;
+    }
+};
+
+struct Guard {  // make the context's device current for the duration of a call
+    int prev = -1;
+    bool ok = false;
+    explicit Guard(const dfk_ctx* ctx) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~Guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define DFK_ENTER(ctx)                                             \
+    if (!(ctx)) return fail(DFK_ERR_ARG, "null context");          \
+    Guard guard_(ctx);                                             \
+    if (!guard_.ok) return fail(DFK_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
+dfk::LmOpts to_opts(const dfk_lm_opts* o) {
+    dfk_lm_opts d;
+    if (!o) {
+        dfk_default_lm_opts(&d);
+        o = &d;
+    }
+    dfk::LmOpts r;
+    r.max_steps = o->max_lma_steps;
+    r.conv_improve = o->conv_improve;
+    r.conv_param = o->conv_param;
+    r.fitok_threshold = o->fitok_threshold;
+    r.grid_min = o->m_grid_min;
+    r.grid_max = o->m_grid_max;
+    r.grid_step = o->m_grid_step;
+    r.bessel_thr = o->bessel_amp_threshold;
+    r.sincos_thr = o->sincos_amp_threshold;
+    return r;
+}
+
+// ---- demodulation -------------------------------------------------------------------------------
+struct FoldGeometry {
+    int pps, nstages;
+    size_t smem;
+    int ctas_per_sm;
+};
+
+bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeometry* g) {
+    const int P = static_cast<int>(pl.P);
+    int pps = dfk::kFoldStageBytes / (P * 8);
+    if (pps < 1) pps = 1;
+    if (pps > pl.periods) pps = static_cast<int>(pl.periods);
+    // prefer two resident CTAs per SM (one folds while the other takes harmonics) with a ring of
+    // 3..6 stages; fall back to one CTA per SM with whatever ring fits
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        const size_t budget = ctas == 2 ? static_cast<size_t>(ctx->smem_per_sm) / 2 - 1024
+                                        : static_cast<size_t>(ctx->max_smem_optin);
+        for (int nst = 6; nst >= (ctas == 2 ? 3 : 2); --nst) {
+            const dfk::FoldSmem L = dfk::fold_smem_layout(P, pps, nst, N, pl.drift);
+            if (L.total <= budget) {
+                g->pps = pps;
+                g->nstages = nst;
+                g->smem = L.total;
+                g->ctas_per_sm = ctas;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
+int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
+                 double* qi, double* dc, cudaStream_t st) {
+    if (nbuf == 0) return DFK_OK;
+    const dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
+    FoldGeometry g;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
+    if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, &g)) {
+        dfk::FoldParams p;
+        p.x = x;
+        p.qi = qi;
+        p.dc = dc;
+        p.nbuf = nbuf;
+        p.bpc = bpc;
+        p.ld_c = ld_c;
+        p.R = static_cast<int>(R);
+        p.P = static_cast<int>(pl.P);
+        p.periods = static_cast<int>(pl.periods);
+        p.N = N;
+        p.pps = g.pps;
+        p.nstages = g.nstages;
+        for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];
+        const int grid = static_cast<int>(std::min<int64_t>(nbuf, static_cast<int64_t>(ctx->sm_count) * g.ctas_per_sm));
+        if (pl.drift) {
+            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(g.smem)));
+            dfk::demod_fold_kernel<true><<<grid, dfk::kFoldThreads, g.smem, st>>>(p);
+        } else {
+            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(g.smem)));
+            dfk::demod_fold_kernel<false><<<grid, dfk::kFoldThreads, g.smem, st>>>(p);
+        }
+    } else {
+        const int grid = static_cast<int>(std::min<int64_t>(nbuf, static_cast<int64_t>(ctx->sm_count) * 8));
+        dfk::demod_direct_kernel<<<grid, dfk::kDirectThreads, 0, st>>>(x, nbuf, bpc, ld_c, R, N, w0, qi, dc);
+    }
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+// ---- LM -------------------------------------------------------------------------------------------
+int pick_lanes(const dfk_ctx* ctx, int64_t nfit, int N, int requested) {
+    if (requested == 1 || requested == 2 || requested == 4 || requested == 8 || requested == 16 || requested == 32)
+        return requested;
+    // enough groups to give every SM ~1024 resident threads; never more lanes than harmonics can use
+    const int64_t threads_wanted = static_cast<int64_t>(ctx->sm_count) * 1024;
+    int g = 32;
+    while (g > 1 && nfit * g > threads_wanted) g >>= 1;
+    while (g > 1 && g > N) g >>= 1;
+    if (g < 1) g = 1;
+    return g;
+}
+
+template <int G>
+int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
+                 const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    const int64_t fits_per_block = dfk::kLmThreads / G;
+    const int64_t blocks = (nfit + fits_per_block - 1) / fits_per_block;
+    const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * 16));
+    dfk::lm_first_kernel<G><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+int ensure_counters(dfk_ctx* ctx) {
+    if (ctx->counters.ptr) return DFK_OK;
+    const int rc = ensure(ctx, ctx->counters, sizeof(dfk::LmCounts));
+    if (rc) return rc;
+    DFK_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(dfk::LmCounts), ctx->stream()));
+    return DFK_OK;
+}
+
+// first descent for every fit + retry stage for those that stayed above the threshold.
+// max_unit: largest unit index + 1 the launch can touch (sizes the retry list).
+int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs,
+              const double* dc, const dfk_lm_opts* opts, double* rows, cudaStream_t st) {
+    if (nfit == 0) return DFK_OK;
+    const int64_t max_unit = (nfit - 1) * map.step + map.offset + 1;
+    if (max_unit > std::numeric_limits<int>::max()) return fail(DFK_ERR_ARG, "more than 2^31-1 fit units in one call");
+    const dfk::LmOpts o = to_opts(opts);
+    int rc = ensure_counters(ctx);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->retry, (static_cast<size_t>(nfit) + 4) * sizeof(int));
+    if (rc) return rc;
+    int* count = static_cast<int*>(ctx->retry.ptr);
+    int* list = count + 4;
+    auto* counters = static_cast<dfk::LmCounts*>(ctx->counters.ptr);
+    DFK_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    const int G = pick_lanes(ctx, nfit, N, opts ? opts->lanes_per_fit : 0);
+    switch (G) {
+        case 1: rc = launch_first<1>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        case 2: rc = launch_first<2>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        case 4: rc = launch_first<4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        case 8: rc = launch_first<8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        case 16: rc = launch_first<16>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        default: rc = launch_first<32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+    }
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    const int64_t warps = dfk::kLmThreads / 32;
+    const int grid = static_cast<int>(std::min<int64_t>((nfit + warps - 1) / warps, static_cast<int64_t>(ctx->sm_count) * 8));
+    dfk::lm_retry_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, N, o, rows, list, count, counters);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+int check_nls_args(int64_t nbuf, int64_t R, int32_t N, double w0) {
+    if (nbuf < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry: nbuf=%lld R=%lld", (long long)nbuf, (long long)R);
+    if (N < 1 || N > DFK_MAX_HARMONICS) return fail(DFK_ERR_ARG, "harmonic count %d outside 1..%d", N, DFK_MAX_HARMONICS);
+    if (!(w0 > 0.0) || !std::isfinite(w0)) return fail(DFK_ERR_ARG, "w0 must be positive and finite");
+    return DFK_OK;
+}
+
+dfk::GuessSrc guess_value(const double v[4]) {
+    dfk::GuessSrc g;
+    g.ptr = nullptr;
+    g.stride = 0;
+    g.div = 1;
+    g.skip_first = 0;
+    for (int i = 0; i < 4; ++i) g.val[i] = v[i];
+    return g;
+}
+
+dfk::GuessSrc guess_rows(const double* ptr, int64_t stride, int64_t div, bool skip_first) {
+    dfk::GuessSrc g;
+    g.ptr = ptr;
+    g.stride = stride;
+    g.div = div < 1 ? 1 : div;
+    g.skip_first = skip_first ? 1 : 0;
+    for (int i = 0; i < 4; ++i) g.val[i] = 0.0;
+    return g;
+}
+
+// demod + fits of C device-resident channel records of bpc buffers each (records ld_c samples apart).
+//   init_dev == nullptr: every cold start uses init[4]; else channel c starts from init_dev[c * init_stride ..+3].
+//   seeded == 0: every buffer is an independent cold start (workers.py:167-173).
+//   seeded != 0: buffer 0 of each channel is fitted cold, buffers 1.. start from its result
+//                (fitters.py:404-417 at n_cores >= nbuf - 1).  seed_row (single-channel slabs only): the row
+//                that already holds that result from an earlier slab.
+int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
+                  const double init[4], const double* init_dev, int64_t init_stride, int32_t seeded,
+                  const double* seed_row, const dfk_lm_opts* opts, double* rows, cudaStream_t st) {
+    const int64_t nbuf = C * bpc;
+    if (nbuf == 0) return DFK_OK;
+    int rc = ensure(ctx, ctx->qi, static_cast<size_t>(nbuf) * 2 * N * sizeof(double));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->dc, static_cast<size_t>(nbuf) * sizeof(double));
+    if (rc) return rc;
+    double* qi = static_cast<double*>(ctx->qi.ptr);
+    double* dc = static_cast<double*>(ctx->dc.ptr);
+    {
+        ProfScope ps(ctx, 0, st);
+        rc = launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st);
+    }
+    if (rc) return rc;
+    ProfScope ps(ctx, 1, st);
+    const dfk::GuessSrc cold = init_dev ? guess_rows(init_dev, init_stride, bpc, false) : guess_value(init);
+    if (!seeded || (bpc == 1 && !seed_row)) return launch_lm(ctx, qi, nbuf, {1, 0}, N, cold, dc, opts, rows, st);
+    if (seed_row) {  // continuation slab of a single record: everything starts from the stored row
+        return launch_lm(ctx, qi, nbuf, {1, 0}, N, guess_rows(seed_row, 0, nbuf, false), dc, opts, rows, st);
+    }
+    rc = launch_lm(ctx, qi, C, {bpc, 0}, N, cold, dc, opts, rows, st);  // fitters.py:404-405, once per channel
+    if (rc) return rc;
+    // fitters.py:407-417: every other buffer starts from its channel's buffer-0 result
+    return launch_lm(ctx, qi, nbuf, {1, 0}, N, guess_rows(rows, bpc * DFK_ROW_STRIDE, bpc, true), dc, opts, rows, st);
+}
+
+}  // namespace
+
+// ==================================================================================================
+extern "C" {
+
+int dfk_abi_version(void) { return DFK_ABI_VERSION; }
+
+const char* dfk_last_error(void) { return g_err; }
+
+int dfk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void dfk_default_lm_opts(dfk_lm_opts* o) {
+    if (!o) return;
+    o->max_lma_steps = 100;
+    o->lanes_per_fit = 0;
+    o->conv_improve = 1e-9;
+    o->conv_param = 1e-9;
+    o->fitok_threshold = 1e-3;
+    o->m_grid_min = 5.0;
+    o->m_grid_max = 30.0;
+    o->m_grid_step = 0.5;
+    o->bessel_amp_threshold = 0.05;
+    o->sincos_amp_threshold = 0.1;
+}
+
+void dfk_default_ekf_opts(dfk_ekf_opts* o) {
+    if (!o) return;
+    const double init[4] = {1.6, 6.0, 0.0, 0.0};
+    const double q[5] = {1e-8, 1e-8, 1e-6, 1e-6, 1e-8};
+    for (int i = 0; i < 4; ++i) o->init[i] = init[i];
+    for (int i = 0; i < 5; ++i) {
+        o->p0_diag[i] = 1.0;
+        o->q_diag[i] = q[i];
+    }
+    o->r_val = std::numeric_limits<double>::quiet_NaN();
+}
+
+int dfk_create(int device, dfk_ctx** out) {
+    if (!out) return fail(DFK_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(DFK_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(DFK_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    DFK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(DFK_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    dfk_ctx* ctx = new (std::nothrow) dfk_ctx();
+    if (!ctx) return fail(DFK_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    ctx->smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
+    Guard g(ctx);
+    if (!g.ok) {
+        delete ctx;
+        return fail(DFK_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->consumed[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        dfk_destroy(ctx);
+        return fail(DFK_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return DFK_OK;
+}
+
+int dfk_destroy(dfk_ctx* ctx) {
+    if (!ctx) return DFK_OK;
+    Guard g(ctx);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    DevBuf* bufs[] = {&ctx->qi, &ctx->dc, &ctx->retry, &ctx->counters, &ctx->slab[0], &ctx->slab[1],
+                      &ctx->rows, &ctx->stats, &ctx->misc};
+    for (DevBuf* b : bufs)
+        if (b->ptr) cudaFree(b->ptr);
+    for (auto& kind : ctx->prof_ev)
+        for (auto& pair : kind)
+            for (cudaEvent_t ev : pair)
+                if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->copied[i]) cudaEventDestroy(ctx->copied[i]);
+        if (ctx->consumed[i]) cudaEventDestroy(ctx->consumed[i]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return DFK_OK;
+}
+
+int dfk_set_stream(dfk_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(DFK_ERR_ARG, "null context");
+    ctx->user_stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->use_user = cuda_stream != nullptr;
+    return DFK_OK;
+}
+
+int dfk_use_legacy_default_stream(dfk_ctx* ctx, int on) {
+    if (!ctx) return fail(DFK_ERR_ARG, "null context");
+    ctx->user_stream = nullptr;  // the legacy default stream is the null handle
+    ctx->use_user = on != 0;
+    return DFK_OK;
+}
+
+int dfk_synchronize(dfk_ctx* ctx) {
+    DFK_ENTER(ctx);
+    DFK_CUDA(cudaStreamSynchronize(ctx->stream()));
+    return DFK_OK;
+}
+
+int dfk_demod(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0, double* qi_dev,
+              double* dc_dev) {
+    DFK_ENTER(ctx);
+    const int rc = check_nls_args(nbuf, R, N, w0);
+    if (rc) return rc;
+    if (nbuf > 0 && (!x_dev || !qi_dev || !dc_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    return launch_demod(ctx, x_dev, nbuf, nbuf, nbuf * R, R, N, w0, qi_dev, dc_dev, ctx->stream());
+}
+
+int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, const double* guess_dev,
+               int64_t guess_stride, const double* dc_dev, const dfk_lm_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    if (nbuf < 0) return fail(DFK_ERR_ARG, "negative fit count");
+    if (N < 1 || N > DFK_MAX_HARMONICS) return fail(DFK_ERR_ARG, "harmonic count %d outside 1..%d", N, DFK_MAX_HARMONICS);
+    if (nbuf > 0 && (!qi_dev || !guess_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    if (guess_stride != 0 && guess_stride < 4) return fail(DFK_ERR_ARG, "guess_stride must be 0 or >= 4");
+    const dfk::GuessSrc gs = guess_stride == 0 ? guess_rows(guess_dev, 0, nbuf, false) : guess_rows(guess_dev, guess_stride, 1, false);
+    return launch_lm(ctx, qi_dev, nbuf, {1, 0}, N, gs, dc_dev, opts, rows_dev, ctx->stream());
+}
+
+int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
+                    const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    const int rc = check_nls_args(nbuf, R, N, w0);
+    if (rc) return rc;
+    if (!init) return fail(DFK_ERR_ARG, "null init");
+    if (nbuf > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, init, nullptr, 0, seeded, nullptr, opts, rows_dev,
+                         ctx->stream());
+}
+
+int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t ld_c,
+                          int64_t R, int32_t N, double w0, const double init[4], const double* init_dev,
+                          int64_t init_stride, int32_t seeded, const dfk_lm_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    if (C < 0 || bufs_per_channel < 0) return fail(DFK_ERR_ARG, "negative channel or buffer count");
+    const int rc = check_nls_args(C * bufs_per_channel, R, N, w0);
+    if (rc) return rc;
+    if (ld_c < bufs_per_channel * R) return fail(DFK_ERR_ARG, "channel stride shorter than the channel record");
+    if (!init && !init_dev) return fail(DFK_ERR_ARG, "no initial guess");
+    if (init_dev && init_stride < 4) return fail(DFK_ERR_ARG, "init_stride must be >= 4");
+    if (C * bufs_per_channel > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    const double zero[4] = {0, 0, 0, 0};
+    return nls_on_device(ctx, x_dev, C, bufs_per_channel, ld_c, R, N, w0, init ? init : zero, init_dev, init_stride,
+                         seeded, nullptr, opts, rows_dev, ctx->stream());
+}
+
+int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                     const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_host) {
+    DFK_ENTER(ctx);
+    if (nsamp < 0) return fail(DFK_ERR_ARG, "negative sample count");
+    const int64_t nbuf = R > 0 ? nsamp / R : 0;
+    int rc = check_nls_args(nbuf, R, N, w0);
+    if (rc) return rc;
+    if (!init) return fail(DFK_ERR_ARG, "null init");
+    if (nbuf == 0) return DFK_OK;
+    if (!x_host || !rows_host) return fail(DFK_ERR_ARG, "null host pointer");
+    // slabs of whole buffers, ~128 MiB each, double buffered: the copy of slab i+1 overlaps the
+    // kernels of slab i.  (A record that fits one slab is a single copy.)
+    const int64_t slab_buffers = std::max<int64_t>(1, std::min<int64_t>(nbuf, (128ll << 20) / (R * 8)));
+    const size_t slab_bytes = static_cast<size_t>(slab_buffers) * R * 8;
+    const int nslab_bufs = nbuf > slab_buffers ? 2 : 1;
+    for (int i = 0; i < nslab_bufs; ++i) {
+        rc = ensure(ctx, ctx->slab[i], slab_bytes);
+        if (rc) return rc;
+    }
+    rc = ensure(ctx, ctx->rows, static_cast<size_t>(nbuf) * DFK_ROW_STRIDE * sizeof(double));
+    if (rc) return rc;
+    // scratch for one slab, sized up front so that no reallocation happens mid-pipeline
+    rc = ensure(ctx, ctx->qi, static_cast<size_t>(slab_buffers) * 2 * N * sizeof(double));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->dc, static_cast<size_t>(slab_buffers) * sizeof(double));
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->retry, (static_cast<size_t>(slab_buffers) + 4) * sizeof(int));
+    if (rc) return rc;
+    double* rows = static_cast<double*>(ctx->rows.ptr);
+    cudaStream_t st = ctx->stream();
+    int64_t done = 0;
+    for (int64_t i = 0; done < nbuf; ++i) {
+        const int sl = static_cast<int>(i & 1);
+        const int64_t nb = std::min(slab_buffers, nbuf - done);
+        double* dst = static_cast<double*>(ctx->slab[sl].ptr);
+        if (i >= 2) DFK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->consumed[sl], 0));
+        DFK_CUDA(cudaMemcpyAsync(dst, x_host + done * R, static_cast<size_t>(nb) * R * 8, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+        DFK_CUDA(cudaEventRecord(ctx->copied[sl], ctx->copy_stream));
+        DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[sl], 0));
+        rc = nls_on_device(ctx, dst, 1, nb, nb * R, R, N, w0, init, nullptr, 0, seeded,
+                           (seeded && done > 0) ? rows : nullptr, opts, rows + done * DFK_ROW_STRIDE, st);
+        if (rc) return rc;
+        DFK_CUDA(cudaEventRecord(ctx->consumed[sl], st));
+        done += nb;
+    }
+    DFK_CUDA(cudaMemcpyAsync(rows_host, rows, static_cast<size_t>(nbuf) * DFK_ROW_STRIDE * sizeof(double),
+                             cudaMemcpyDeviceToHost, st));
+    DFK_CUDA(cudaStreamSynchronize(st));
+    return DFK_OK;
+}
+
+int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c, int64_t R,
+                double f_samp, double f_mod, const dfk_ekf_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    if (T < 0 || C < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry: T=%lld C=%lld R=%lld", (long long)T, (long long)C, (long long)R);
+    if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
+    if (T == 0 || C == 0) return DFK_OK;
+    if (!z_dev || !rows_dev) return fail(DFK_ERR_ARG, "null device pointer");
+    dfk_ekf_opts d;
+    if (!opts) {
+        dfk_default_ekf_opts(&d);
+        opts = &d;
+    }
+    int rc = ensure(ctx, ctx->stats, static_cast<size_t>(C) * 2 * sizeof(double));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream();
+    double* stats = static_cast<double*>(ctx->stats.ptr);
+    const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
+    dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    dfk::EkfLaunch a;
+    for (int i = 0; i < 4; ++i) a.init[i] = opts->init[i];
+    for (int i = 0; i < 5; ++i) {
+        a.p0[i] = opts->p0_diag[i];
+        a.q[i] = opts->q_diag[i];
+    }
+    a.r_val = opts->r_val;
+    a.w_m = 2 * dfk::kPi * f_mod;  // fitters.py:262
+    a.f_samp = f_samp;
+    const int grid = static_cast<int>((C + dfk::kEkfThreads - 1) / dfk::kEkfThreads);
+    dfk::ekf_kernel<<<grid, dfk::kEkfThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64_t R, double f_samp, double f_mod,
+                 const dfk_ekf_opts* opts, double* rows_host) {
+    DFK_ENTER(ctx);
+    if (T < 0 || C < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry");
+    const int64_t nbuf = T / R;
+    if (T == 0 || C == 0) return DFK_OK;
+    if (!z_host || (nbuf > 0 && !rows_host)) return fail(DFK_ERR_ARG, "null host pointer");
+    int rc = ensure(ctx, ctx->slab[0], static_cast<size_t>(T) * C * 8);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->rows, std::max<size_t>(8, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream();
+    DFK_CUDA(cudaMemcpyAsync(ctx->slab[0].ptr, z_host, static_cast<size_t>(T) * C * 8, cudaMemcpyHostToDevice, st));
+    rc = dfk_ekf_dev(ctx, static_cast<const double*>(ctx->slab[0].ptr), T, C, 1, T, R, f_samp, f_mod, opts,
+                     static_cast<double*>(ctx->rows.ptr));
+    if (rc) return rc;
+    if (nbuf > 0)
+        DFK_CUDA(cudaMemcpyAsync(rows_host, ctx->rows.ptr, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8,
+                                 cudaMemcpyDeviceToHost, st));
+    DFK_CUDA(cudaStreamSynchronize(st));
+    return DFK_OK;
+}
+
+int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double f_samp, double f_mod, double m,
+                      double amp, double visibility, double phi0, double dphi, double psi0, double snr_db,
+                      uint64_t seed) {
+    DFK_ENTER(ctx);
+    if (T < 0 || C < 0) return fail(DFK_ERR_ARG, "bad geometry");
+    if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
+    if (T == 0 || C == 0) return DFK_OK;
+    if (!x_dev) return fail(DFK_ERR_ARG, "null device pointer");
+    dfk::SynthParams p;
+    p.x = x_dev;
+    p.T = T;
+    p.C = C;
+    const double per = f_samp / f_mod;
+    p.P = (per == std::floor(per) && per >= 1.0 && per < 9e15) ? static_cast<long long>(per) : 0;
+    p.f_ratio = f_mod / f_samp;
+    p.m = m;
+    p.amp = amp;
+    p.vis = visibility;
+    p.phi0 = phi0;
+    p.dphi = dphi;
+    p.psi0 = psi0;
+    p.sigma_scale = std::pow(10.0, -snr_db / 20.0);
+    p.seed = seed;
+    const int64_t pairs = ((T + 1) / 2) * C;
+    const int grid = static_cast<int>(std::min<int64_t>((pairs + 255) / 256, static_cast<int64_t>(ctx->sm_count) * 32));
+    dfk::synth_snr_kernel<<<grid, 256, 0, ctx->stream()>>>(p);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset) {
+    DFK_ENTER(ctx);
+    if (!out) return fail(DFK_ERR_ARG, "null output pointer");
+    const int rc = ensure_counters(ctx);
+    if (rc) return rc;
+    static_assert(sizeof(dfk_lm_counters) == sizeof(dfk::LmCounts), "counter layouts must agree");
+    DFK_CUDA(cudaMemcpyAsync(out, ctx->counters.ptr, sizeof(dfk_lm_counters), cudaMemcpyDeviceToHost, ctx->stream()));
+    if (reset) DFK_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(dfk::LmCounts), ctx->stream()));
+    DFK_CUDA(cudaStreamSynchronize(ctx->stream()));
+    return DFK_OK;
+}
+
+int dfk_profile_enable(dfk_ctx* ctx, int32_t on) {
+    DFK_ENTER(ctx);
+    if (!on) {
+        const int rc = prof_drain(ctx);
+        if (rc) return rc;
+    }
+    ctx->profiling = on != 0;
+    return DFK_OK;
+}
+
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int32_t reset) {
+    DFK_ENTER(ctx);
+    if (!ms_total || !launches) return fail(DFK_ERR_ARG, "null output pointer");
+    const int rc = prof_drain(ctx);
+    if (rc) return rc;
+    for (int k = 0; k < 2; ++k) {
+        ms_total[k] = ctx->prof_ms[k];
+        launches[k] = ctx->prof_n[k];
+        if (reset) {
+            ctx->prof_ms[k] = 0.0;
+            ctx->prof_n[k] = 0;
+        }
+    }
+    return DFK_OK;
+}
+
+int64_t dfk_launch_count(dfk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dfk_demod_path(int64_t R, double w0) {
+    const dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, 1);
+    return pl.folded ? 1 : 0;
+}
+
+int dfk_bessel_dev(dfk_ctx* ctx, const double* x_dev, int64_t n, int32_t nmax, double* out_dev) {
+    DFK_ENTER(ctx);
+    if (n < 0 || nmax < 0 || nmax > DFK_MAX_HARMONICS + 1) return fail(DFK_ERR_ARG, "bad arguments");
+    if (n == 0) return DFK_OK;
+    if (!x_dev || !out_dev) return fail(DFK_ERR_ARG, "null device pointer");
+    dfk::bessel_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, ctx->stream()>>>(x_dev, n, nmax, out_dev);
+    ctx->launches++;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
+}  // extern "C"

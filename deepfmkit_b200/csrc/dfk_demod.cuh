@@ -1,0 +1,339 @@
+// Lock-in demodulation kernels (sm_100a).
+//
+// Reference computation (fit.py:55-64 + fitters.py:45-49,57): per buffer of R samples,
+//   Q_k = mean(x[t] * cos(fl((k)*w0)*t)),  I_k = mean(x[t] * sin(fl(k*w0)*t)),  k = 1..N,  dc = mean(x),
+// with t restarting at 0 in every buffer.
+//
+// demod_fold_kernel -- the bandwidth-bound path.  Needs a whole even number P of samples per modulation
+//   period and whole periods per buffer (dfk_demod_plan.h).  A persistent CTA streams its buffers from HBM
+//   with 1-D TMA bulk copies (cp.async.bulk, one elected producer lane, mbarrier ring) and folds the
+//   periods onto one: S_j = sum_c x[j + cP] -- one DADD per 8 bytes (plus one DFMA for the drift sum).
+//   The N harmonics are then taken from the folded period with the j <-> P-j symmetry
+//   (cos(k th_j) even, sin(k th_j) odd) by a rotation recurrence per lane and a warp-shuffle reduction.
+//   Every sample is read from HBM exactly once: 8 B/sample + 8(2N+1) B/buffer written.
+//
+// demod_direct_kernel -- any R and w0 (non-integer period): one CTA per buffer, harmonics in blocks of
+//   kDirectKB with a per-thread rotation recurrence re-synchronised with sincos every kDirectResync
+//   steps.  Compute-bound (6 fp64 ops per sample and harmonic); later harmonic blocks re-read the
+//   buffer from L1/L2.
+#pragma once
+#include "dfk_common.cuh"
+#include "dfk_demod_plan.h"
+
+namespace dfk {
+
+constexpr int kFoldConsumerWarps = 8;
+constexpr int kFoldConsumers = kFoldConsumerWarps * 32;  // 256
+constexpr int kFoldThreads = kFoldConsumers + 32;        // + producer warp
+constexpr int kFoldStageBytes = 16384;
+constexpr int kFoldMaxSlots = static_cast<int>(kMaxFoldPeriod / 2 / kFoldConsumers);  // column pairs per thread (4)
+
+struct FoldParams {
+    const double* x;
+    double* qi;
+    double* dc;
+    long long nbuf;
+    long long bpc;   // buffers per channel record
+    long long ld_c;  // samples between the starts of consecutive channel records
+    int R, P, periods, N;
+    int pps;      // periods per pipeline stage
+    int nstages;  // ring depth
+    double delta[kMaxHarmonics];
+};
+
+// shared-memory carve-up, identical on host (size) and device (pointers)
+struct FoldSmem {
+    int stage_doubles;  // pps * P
+    size_t off_stage, off_s, off_u, off_cmb, off_tw, off_step, off_bar, total;
+};
+
+inline __host__ __device__ FoldSmem fold_smem_layout(int P, int pps, int nstages, int N, bool drift) {
+    FoldSmem L;
+    L.stage_doubles = pps * P;
+    size_t o = 0;
+    L.off_stage = o;
+    o += static_cast<size_t>(nstages) * L.stage_doubles * 8;
+    L.off_s = o;
+    o += static_cast<size_t>(P) * 8;
+    L.off_u = o;
+    o += drift ? static_cast<size_t>(P) * 8 : 0;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    L.off_cmb = o;
+    o += static_cast<size_t>(P / 2 + 1) * (drift ? 32 : 16);
+    L.off_tw = o;
+    o += static_cast<size_t>(N + 1) * 32 * 16;
+    L.off_step = o;
+    o += static_cast<size_t>(N + 1) * 16;
+    L.off_bar = o;
+    o += static_cast<size_t>(2 * nstages) * 8;
+    L.total = o;
+    return L;
+}
+
+DFK_D void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kFoldConsumers) : "memory"); }
+
+DFK_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+template <bool DRIFT>
+__global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FoldSmem L = fold_smem_layout(p.P, p.pps, p.nstages, p.N, DRIFT);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
+    double* sm_s = reinterpret_cast<double*>(smem_raw + L.off_s);
+    double* sm_u = reinterpret_cast<double*>(smem_raw + L.off_u);
+    double* sm_cmb = reinterpret_cast<double*>(smem_raw + L.off_cmb);
+    double2* sm_tw = reinterpret_cast<double2*>(smem_raw + L.off_tw);
+    double2* sm_step = reinterpret_cast<double2*>(smem_raw + L.off_step);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* empty = full + p.nstages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, N = p.N, half = P >> 1;
+    const int chunks = (p.periods + p.pps - 1) / p.pps;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFoldConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    // twiddles: start value for (harmonic k, lane) and the 32-column step of harmonic k; the same
+    // for every buffer because the lock-in phase restarts at each buffer.
+    for (int i = tid; i < (N + 1) * 32; i += kFoldThreads) {
+        const int k = i >> 5, l = i & 31;
+        const long long r = (static_cast<long long>(k) * l) % P;
+        double s, c;
+        sincospi(2.0 * static_cast<double>(r) / static_cast<double>(P), &s, &c);
+        sm_tw[i] = make_double2(c, s);
+    }
+    for (int k = tid; k <= N; k += kFoldThreads) {
+        const long long r = (static_cast<long long>(k) * 32) % P;
+        double s, c;
+        sincospi(2.0 * static_cast<double>(r) / static_cast<double>(P), &s, &c);
+        sm_step[k] = make_double2(c, s);
+    }
+    __syncthreads();
+
+    if (warp == kFoldConsumerWarps) {
+        // ---------------- producer: one lane feeds the ring -----------------------------------
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long b = blockIdx.x; b < p.nbuf; b += gridDim.x) {
+                const double* src = p.x + (b / p.bpc) * p.ld_c + (b % p.bpc) * static_cast<long long>(p.R);
+                for (int q = 0; q < chunks; ++q) {
+                    const int np = min(p.pps, p.periods - q * p.pps);
+                    const uint32_t bytes = static_cast<uint32_t>(np) * static_cast<uint32_t>(P) * 8u;
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    bulk_load(stage_base + static_cast<size_t>(stage) * L.stage_doubles,
+                              src + static_cast<size_t>(q) * p.pps * P, bytes, &full[stage], pol);
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: fold, then harmonics -----------------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long b = blockIdx.x; b < p.nbuf; b += gridDim.x) {
+        double2 accS[kFoldMaxSlots], accT[kFoldMaxSlots];
+#pragma unroll
+        for (int s = 0; s < kFoldMaxSlots; ++s) {
+            accS[s] = make_double2(0.0, 0.0);
+            accT[s] = make_double2(0.0, 0.0);
+        }
+        for (int q = 0; q < chunks; ++q) {
+            const int np = min(p.pps, p.periods - q * p.pps);
+            mbar_wait(&full[stage], phase);
+            const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+            for (int c = 0; c < np; ++c) {
+                const double2* row = reinterpret_cast<const double2*>(sm + c * P);
+                const double cg = static_cast<double>(q * p.pps + c);
+#pragma unroll
+                for (int s = 0; s < kFoldMaxSlots; ++s) {
+                    const int pair = tid + s * kFoldConsumers;
+                    if (pair < half) {
+                        const double2 v = row[pair];
+                        accS[s].x += v.x;
+                        accS[s].y += v.y;
+                        if (DRIFT) {
+                            accT[s].x = fma(cg, v.x, accT[s].x);
+                            accT[s].y = fma(cg, v.y, accT[s].y);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == p.nstages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+
+        consumer_bar();  // everyone is done with the previous buffer's folded arrays
+#pragma unroll
+        for (int s = 0; s < kFoldMaxSlots; ++s) {
+            const int pair = tid + s * kFoldConsumers;
+            if (pair < half) {
+                reinterpret_cast<double2*>(sm_s)[pair] = accS[s];
+                if (DRIFT) {
+                    // U_j = sum_c (j + cP) x[j + cP] = j S_j + P T_j
+                    const double j0 = static_cast<double>(2 * pair);
+                    const double Pd = static_cast<double>(P);
+                    reinterpret_cast<double2*>(sm_u)[pair] =
+                        make_double2(fma(Pd, accT[s].x, j0 * accS[s].x), fma(Pd, accT[s].y, (j0 + 1.0) * accS[s].y));
+                }
+            }
+        }
+        consumer_bar();
+        // symmetric / antisymmetric combinations over j <-> P - j  (j = 0 and j = P/2 pair with nothing)
+        for (int j = tid; j <= half; j += kFoldConsumers) {
+            const bool self = (j == 0) || (j == half);
+            const double sa = sm_s[j], sb = self ? 0.0 : sm_s[P - j];
+            if (DRIFT) {
+                const double ua = sm_u[j], ub = self ? 0.0 : sm_u[P - j];
+                reinterpret_cast<double2*>(sm_cmb)[2 * j] = make_double2(sa + sb, self ? 0.0 : sa - sb);
+                reinterpret_cast<double2*>(sm_cmb)[2 * j + 1] = make_double2(ua + ub, self ? 0.0 : ua - ub);
+            } else {
+                reinterpret_cast<double2*>(sm_cmb)[j] = make_double2(sa + sb, self ? 0.0 : sa - sb);
+            }
+        }
+        consumer_bar();
+
+        // harmonic k (k = 0 is the mean) is owned by warp k % 8; lanes stride the half period by 32
+        const double Rd = static_cast<double>(p.R);
+        for (int k = warp; k <= N; k += kFoldConsumerWarps) {
+            const double2 w0 = sm_tw[k * 32 + lane];
+            const double2 st = sm_step[k];
+            double c = w0.x, s = w0.y;
+            double aq = 0.0, ai = 0.0, aqu = 0.0, aiu = 0.0;
+            for (int j = lane; j <= half; j += 32) {
+                if (DRIFT) {
+                    const double2 ab = reinterpret_cast<const double2*>(sm_cmb)[2 * j];
+                    const double2 uab = reinterpret_cast<const double2*>(sm_cmb)[2 * j + 1];
+                    aq = fma(ab.x, c, aq);
+                    ai = fma(ab.y, s, ai);
+                    aqu = fma(uab.y, s, aqu);
+                    aiu = fma(uab.x, c, aiu);
+                } else {
+                    const double2 ab = reinterpret_cast<const double2*>(sm_cmb)[j];
+                    aq = fma(ab.x, c, aq);
+                    ai = fma(ab.y, s, ai);
+                }
+                const double cn = c * st.x - s * st.y;
+                s = fma(s, st.x, c * st.y);
+                c = cn;
+            }
+            aq = warp_sum(aq);
+            if (k > 0) {
+                ai = warp_sum(ai);
+                if (DRIFT) {
+                    aqu = warp_sum(aqu);
+                    aiu = warp_sum(aiu);
+                }
+            }
+            if (lane == 0) {
+                if (k == 0) {
+                    p.dc[b] = aq / Rd;
+                } else {
+                    double qv = aq, iv = ai;
+                    if (DRIFT) {
+                        const double d = p.delta[k - 1];
+                        qv = fma(-d, aqu, qv);
+                        iv = fma(d, aiu, iv);
+                    }
+                    double* out = p.qi + b * static_cast<long long>(2 * N);
+                    out[k - 1] = qv / Rd;
+                    out[N + k - 1] = iv / Rd;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDirectThreads = 256;
+constexpr int kDirectKB = 8;
+constexpr int kDirectResync = 64;
+
+__global__ void __launch_bounds__(kDirectThreads) demod_direct_kernel(const double* __restrict__ x, long long nbuf,
+                                                                      long long bpc, long long ld_c, long long R, int N,
+                                                                      double w0, double* __restrict__ qi,
+                                                                      double* __restrict__ dc) {
+    __shared__ double red[kDirectThreads / 32][2 * kDirectKB + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (long long b = blockIdx.x; b < nbuf; b += gridDim.x) {
+        const double* buf = x + (b / bpc) * ld_c + (b % bpc) * R;
+        for (int k0 = 0; k0 < N; k0 += kDirectKB) {
+            double aq[kDirectKB], ai[kDirectKB];
+#pragma unroll
+            for (int kk = 0; kk < kDirectKB; ++kk) aq[kk] = ai[kk] = 0.0;
+            double asum = 0.0;
+            for (long long t0 = tid; t0 < R; t0 += static_cast<long long>(kDirectThreads) * kDirectResync) {
+                double c[kDirectKB], s[kDirectKB], cs[kDirectKB], ss[kDirectKB];
+#pragma unroll
+                for (int kk = 0; kk < kDirectKB; ++kk) {
+                    // the reference forms the angle as fl(fl((k)*w0) * t)  (fit.py:59)
+                    const double wk = static_cast<double>(k0 + kk + 1) * w0;
+                    sincos(wk * static_cast<double>(t0), &s[kk], &c[kk]);
+                    sincos(wk * static_cast<double>(kDirectThreads), &ss[kk], &cs[kk]);
+                }
+                long long t = t0;
+                for (int i = 0; i < kDirectResync && t < R; ++i, t += kDirectThreads) {
+                    const double v = __ldg(buf + t);
+                    asum += v;
+#pragma unroll
+                    for (int kk = 0; kk < kDirectKB; ++kk) {
+                        aq[kk] = fma(v, c[kk], aq[kk]);
+                        ai[kk] = fma(v, s[kk], ai[kk]);
+                        const double cn = c[kk] * cs[kk] - s[kk] * ss[kk];
+                        s[kk] = fma(s[kk], cs[kk], c[kk] * ss[kk]);
+                        c[kk] = cn;
+                    }
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < kDirectKB; ++kk) {
+                aq[kk] = warp_sum(aq[kk]);
+                ai[kk] = warp_sum(ai[kk]);
+            }
+            asum = warp_sum(asum);
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < kDirectKB; ++kk) {
+                    red[warp][kk] = aq[kk];
+                    red[warp][kDirectKB + kk] = ai[kk];
+                }
+                red[warp][2 * kDirectKB] = asum;
+            }
+            __syncthreads();
+            if (tid <= 2 * kDirectKB) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < kDirectThreads / 32; ++w) v += red[w][tid];
+                v /= static_cast<double>(R);
+                if (tid == 2 * kDirectKB) {
+                    if (k0 == 0) dc[b] = v;
+                } else {
+                    const int kk = tid % kDirectKB;
+                    if (k0 + kk < N) qi[b * 2 * N + (tid < kDirectKB ? 0 : N) + k0 + kk] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dfk

@@ -27,7 +27,7 @@ struct Coop {
 #if defined(__CUDA_ARCH__)
         if (G == 32) return 0xffffffffu;
         const unsigned lane = threadIdx.x & 31u;
-        return ((1u << G) - 1u) << (lane & ~static_cast<unsigned>(G - 1));
+        return static_cast<unsigned>((1ull << G) - 1ull) << (lane & ~static_cast<unsigned>(G - 1));
 #else
         return 1u;
 #endif

@@ -1,0 +1,142 @@
+// Batched Levenberg-Marquardt kernels around the solver core in dfk_lm_core.cuh.
+//
+// Stage 1 (lm_first_kernel<G>): G lanes per fit run the first descent (fit.py:331).  A fit that ends
+//   below FITOK_THRESHOLD is finished: status 0, normalised, row written.  The others park their
+//   (p, ssq, steps) in the row and append their index to a retry list.
+// Stage 2 (lm_retry_kernel): one warp per parked fit runs the grid-search fallback (51 m candidates
+//   spread over the lanes) and the second descent (fit.py:336-349).  Splitting the stages keeps the
+//   20-40x more expensive fallback from stalling warps whose other fits converged at once.
+//
+// Bessel columns live in shared memory, one column per thread (index k * blockDim.x + threadIdx.x), so
+// the Miller recurrence -- evaluated redundantly by the lanes of a group -- never conflicts on banks.
+#pragma once
+#include "dfk_lm_core.cuh"
+
+namespace dfk {
+
+constexpr int kLmThreads = 128;
+constexpr int kRowStride = 8;
+
+// Where fit number f of a launch finds its data: unit u = f * step + offset indexes qi (u * 2N), dc (u) and
+// rows (u * 8); the initial guess is val, or ptr[(u / div) * stride .. +3].  With div = buffers per channel
+// and ptr = the row table this is "seed every buffer from its channel's buffer 0" (fitters.py:404-417);
+// skip_first then leaves units with u % div == 0 (already fitted) alone.
+struct GuessSrc {
+    const double* ptr;  // nullptr -> val
+    long long stride;   // doubles between consecutive guesses
+    long long div;      // units sharing one guess (>= 1)
+    int skip_first;
+    double val[4];
+};
+
+struct FitMap {
+    long long step, offset;
+};
+
+DFK_D void flush_counts(const LmCounts& c, LmCounts* global, bool leader) {
+    // leaders of each group hold the counts; sum over the warp, one atomic per counter per warp
+    unsigned long long v[5] = {leader ? c.n_state : 0ull, leader ? c.n_ssq : 0ull, leader ? c.n_solve : 0ull,
+                               leader ? c.n_grid : 0ull, leader ? c.n_bessel_steps : 0ull};
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&global->n_state, v[0]);
+        atomicAdd(&global->n_ssq, v[1]);
+        atomicAdd(&global->n_solve, v[2]);
+        atomicAdd(&global->n_grid, v[3]);
+        atomicAdd(&global->n_bessel_steps, v[4]);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kLmThreads) lm_first_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
+                                                              int N, GuessSrc guess, const double* __restrict__ dc,
+                                                              LmOpts o, double* rows,
+                                                              int* __restrict__ retry_list, int* __restrict__ retry_count,
+                                                              LmCounts* __restrict__ counts) {
+    extern __shared__ double bes_smem[];
+    constexpr int kFitsPerBlock = kLmThreads / G;
+    const int group = threadIdx.x / G;
+    const int rank = threadIdx.x & (G - 1);
+    double* bes = bes_smem + threadIdx.x;
+    LmCounts cnt = {};
+    const long long nblocks_work = (nfit + kFitsPerBlock - 1) / kFitsPerBlock;
+    for (long long blk = blockIdx.x; blk < nblocks_work; blk += gridDim.x) {
+        const long long f = blk * kFitsPerBlock + group;
+        // groups past the end still walk the code with fit 0's data so that full-mask shuffles of
+        // G == 32 stay convergent; they write nothing.
+        const long long u = (f < nfit ? f : 0) * map.step + map.offset;
+        const bool live = f < nfit && !(guess.skip_first && (u % guess.div) == 0);
+        const double* q = qi + u * 2 * N;
+        double p[4];
+        if (guess.ptr) {
+            const double* g = guess.ptr + (u / guess.div) * guess.stride;
+            p[0] = g[0]; p[1] = g[1]; p[2] = g[2]; p[3] = g[3];
+        } else {
+            p[0] = guess.val[0]; p[1] = guess.val[1]; p[2] = guess.val[2]; p[3] = guess.val[3];
+        }
+        int steps = 0;
+        LmCounts local = {};
+        const double ssq = lm_descend<G>(N, q, 1, bes, kLmThreads, o, p, steps, local);
+        if (live) {
+            cnt.n_state += local.n_state; cnt.n_ssq += local.n_ssq; cnt.n_solve += local.n_solve;
+            cnt.n_bessel_steps += local.n_bessel_steps;
+        }
+        if (live && rank == 0) {
+            double* row = rows + u * kRowStride;
+            const bool done = ssq < o.fitok_threshold;
+            if (done) normalise_params(p);
+            row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
+            row[4] = dc ? dc[u] : 0.0;
+            row[5] = ssq;
+            row[6] = done ? 0.0 : -1.0;  // -1: parked for the retry stage
+            row[7] = static_cast<double>(steps);
+            if (!done) retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
+        }
+    }
+    flush_counts(cnt, counts, rank == 0);
+}
+
+// retry_list holds unit indices (into qi and rows alike).
+__global__ void __launch_bounds__(kLmThreads) lm_retry_kernel(const double* __restrict__ qi, int N, LmOpts o,
+                                                              double* __restrict__ rows,
+                                                              const int* __restrict__ retry_list,
+                                                              const int* __restrict__ retry_count,
+                                                              LmCounts* __restrict__ counts) {
+    extern __shared__ double bes_smem[];
+    double* bes = bes_smem + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = kLmThreads / 32;
+    const int n = *retry_count;
+    LmCounts cnt = {};
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+        const long long f = retry_list[i];
+        double* row = rows + f * kRowStride;
+        const double* q = qi + f * 2 * N;
+        double p[4] = {row[0], row[1], row[2], row[3]};
+        double ssq = row[5];
+        int steps = static_cast<int>(row[7]);
+        __syncwarp();
+        const int status = retry_fit<32>(N, q, 1, bes, kLmThreads, o, p, ssq, steps, cnt);
+        normalise_params(p);
+        if (lane == 0) {
+            row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
+            row[5] = ssq;
+            row[6] = static_cast<double>(status);
+            row[7] = static_cast<double>(steps);
+        }
+        __syncwarp();
+    }
+    flush_counts(cnt, counts, lane == 0);
+}
+
+// J_0..J_nmax of n arguments, one thread each (testing hook behind dfk_bessel_dev).
+__global__ void bessel_kernel(const double* __restrict__ x, long long n, int nmax, double* __restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) bessel_j_upto(x[i], nmax, out + i * (nmax + 1), 1);
+}
+
+}  // namespace dfk

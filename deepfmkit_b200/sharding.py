@@ -1,0 +1,59 @@
+"""Sharding of fit units (buffers, channels, realisations) over the GPUs of one box.
+
+The readout path has no exchange step: every buffer / channel is independent.  A record
+is cut into contiguous time slabs aligned to buffer boundaries, one per rank; the only shared datum is
+the 4-double seed from buffer 0 (fitters.py:404-417), which rank 0 computes and broadcasts.  Result rows
+are gathered on rank 0 in slab order.  One process per GPU; ``torch.distributed`` (nccl on the GPU box,
+gloo in the CPU tests) is used only for that broadcast and the final gather of the small row table.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def slab_bounds(n_units: int, world_size: int, rank: int):
+    """Contiguous range [lo, hi) of units owned by ``rank``; sizes differ by at most one."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    base, extra = divmod(int(n_units), world_size)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def all_slab_bounds(n_units: int, world_size: int):
+    return [slab_bounds(n_units, world_size, r) for r in range(world_size)]
+
+
+def broadcast_seed(seed_row, src: int = 0, group=None):
+    """Broadcast the 4-double seed (host tensor for gloo, device tensor for nccl) from ``src``."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(np.asarray(seed_row, dtype=np.float64).copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy()
+
+
+def gather_rows(local_rows: np.ndarray, n_units: int, dst: int = 0, group=None):
+    """Gather per-rank row blocks [hi-lo, 8] into one [n_units, 8] table on ``dst`` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bounds = all_slab_bounds(n_units, world)
+    width = local_rows.shape[1] if local_rows.ndim == 2 else 8
+    longest = max(hi - lo for lo, hi in bounds)
+    pad = np.zeros((longest, width), dtype=np.float64)
+    pad[: local_rows.shape[0]] = local_rows
+    t = torch.from_numpy(pad)
+    on_gpu = dist.get_backend(group) == "nccl"
+    if on_gpu:
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = [o.cpu().numpy()[: hi - lo] for o, (lo, hi) in zip(out, bounds)]
+    return np.concatenate(parts, axis=0)

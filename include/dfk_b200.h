@@ -83,6 +83,9 @@ int dfk_destroy(dfk_ctx* ctx);
 /* Use a caller-owned stream (e.g. torch's current stream) for the device-pointer calls;
  * NULL restores the context's own stream. */
 int dfk_set_stream(dfk_ctx* ctx, void* cuda_stream);
+/* on != 0: issue the device-pointer calls on the legacy default stream (handle 0, what torch uses
+ * unless told otherwise); on == 0: back to the context's own stream. */
+int dfk_use_legacy_default_stream(dfk_ctx* ctx, int on);
 int dfk_synchronize(dfk_ctx* ctx);
 void dfk_default_lm_opts(dfk_lm_opts* o);
 void dfk_default_ekf_opts(dfk_ekf_opts* o);
@@ -109,6 +112,16 @@ int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, cons
  * from init (independent single-buffer fits, workers.py:167-173). */
 int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
                     const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
+
+/* The same for C channel records at once (additive API for multi-channel batches and Monte-Carlo
+ * sweeps; the reference loops dff.fit(label) per channel, core.py:279-286).  Channel c is the
+ * bufs_per_channel * R samples at x_dev + c * ld_c.  Cold starts use init[4], or, when init_dev is
+ * not NULL, init_dev[c * init_stride .. +3] (per-channel guesses, e.g. init_m = m_true per grid point,
+ * workers.py:167-173).  seeded != 0: buffer 0 of every channel is fitted cold, its other buffers start
+ * from that result.  rows_dev: C x bufs_per_channel x DFK_ROW_STRIDE. */
+int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t ld_c,
+                          int64_t R, int32_t N, double w0, const double init[4], const double* init_dev,
+                          int64_t init_stride, int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
 
 /* 5-state EKF over C independent channels, one thread per channel.
  * Replaces EKFFitter.fit (fitters.py:214-320).  Sample (t, c) is z_dev[t*ld_t + c*ld_c]
@@ -139,6 +152,12 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
 /* ---- introspection ------------------------------------------------------------------------ */
 /* Counters accumulated by the LM kernels since the last reset (device -> host copy, syncs). */
 int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset);
+/* Device-time accounting per kernel class for the roofline report: with profiling on, the NLS entry
+ * points record CUDA event pairs on the launching stream around the demodulation launch (index 0) and
+ * around the LM launches (index 1).  dfk_profile_read synchronises and returns the summed milliseconds
+ * and the number of timed regions of each class. */
+int dfk_profile_enable(dfk_ctx* ctx, int32_t on);
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int32_t reset);
 /* Kernel launches issued through this context since creation (bench.py's gpu_launches). */
 int64_t dfk_launch_count(dfk_ctx* ctx);
 /* Which demod kernel the given geometry selects: 1 = folded TMA kernel, 0 = general kernel. */

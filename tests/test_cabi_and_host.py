@@ -1,0 +1,184 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/dfk_b200.h declares;
+host-side logic of the fitter API; slab sharding over a 2-rank gloo group.  No compute call is made here
+(the library has no CPU path): anything numerical on the product side is covered by `-m gpu` tests."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from deepfmkit_b200 import _build, _lib
+    _build.build_library()
+    return _lib.load_library()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dfk_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(lib):
+    from deepfmkit_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_struct_layouts_match_header(lib):
+    from deepfmkit_b200 import _lib
+    assert ctypes.sizeof(_lib.LmOpts) == 8 + 8 * 8
+    assert ctypes.sizeof(_lib.EkfOpts) == 15 * 8
+    assert ctypes.sizeof(_lib.LmCounters) == 5 * 8
+    o = _lib.default_lm_opts()
+    assert (o.max_lma_steps, o.conv_improve, o.conv_param, o.fitok_threshold) == (100, 1e-9, 1e-9, 1e-3)
+    assert (o.m_grid_min, o.m_grid_max, o.m_grid_step) == (5.0, 30.0, 0.5)
+    assert (o.bessel_amp_threshold, o.sincos_amp_threshold) == (0.05, 0.1)
+    e = _lib.default_ekf_opts()
+    assert list(e.init) == [1.6, 6.0, 0.0, 0.0] and list(e.p0_diag) == [1.0] * 5
+    assert list(e.q_diag) == [1e-8, 1e-8, 1e-6, 1e-6, 1e-8] and np.isnan(e.r_val)
+
+
+def test_no_gpu_means_loud_failure(lib):
+    """Without a device the product path raises: there is no CPU fallback to fall into."""
+    from deepfmkit_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        _lib.Context(0)
+    from deepfmkit_b200 import DeepRawObject, StandardNLSFitter
+    raw = DeepRawObject(data=np.ones(8000), f_samp=200e3, f_mod=1000)
+    with pytest.raises(RuntimeError):
+        StandardNLSFitter({"n": 20}).fit(raw)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "deepfmkit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "scipy" not in text or f == "dfk_bessel.cuh", f
+
+
+def test_demod_plan_selection(lib):
+    from deepfmkit_b200 import _lib
+    w = lambda fs, fm: 2.0 * np.pi * fm / fs
+    assert _lib.demod_path(4000, w(200e3, 1000.0)) == 1
+    assert _lib.demod_path(20000, w(1e6, 1000.0)) == 1
+    assert _lib.demod_path(200, w(200e3, 1000.0)) == 1
+    assert _lib.demod_path(1500, w(30e3, 400.0)) == 0      # 75 samples per period: odd
+    assert _lib.demod_path(3240, w(200e3, 1234.5)) == 0    # non-integer period
+    assert _lib.demod_path(4100, w(200e3, 1000.0)) == 0    # buffer is not a whole number of periods
+
+
+def test_fitter_host_logic():
+    import pandas as pd
+    from deepfmkit_b200 import BaseFitter, DeepFitFramework, DeepRawObject, StandardNLSFitter, rows_to_frame
+    from deepfmkit_b200.fitters import _calculate_fit_params, _record_values
+    with pytest.raises(ValueError, match="must include 'n'"):
+        StandardNLSFitter({"ndata": 10})
+    with pytest.raises(TypeError):
+        BaseFitter({"n": 1})  # abstract
+    raw = DeepRawObject(data=pd.DataFrame(np.arange(10000.0), columns=["ch0"]), f_samp=200e3, f_mod=1000)
+    assert _calculate_fit_params(raw, 20) == (4000, 50.0, 2)
+    assert _calculate_fit_params(raw, 100)[2] == 0
+    v = _record_values(raw)
+    assert v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (10000,)
+    rows = np.arange(24.0).reshape(3, 8)
+    df = rows_to_frame(rows)
+    assert list(df.columns) == ["amp", "m", "phi", "psi", "dc", "ssq", "fitok"]
+    assert str(df["fitok"].dtype) == "int64" and all(str(df[c].dtype) == "float64" for c in df.columns[:6])
+    dff = DeepFitFramework()
+    dff.load_raw_object(raw, "r")
+    assert dff.fit_init("r", 20) == (4000, 50.0, 2)
+    assert dff.fit("missing") is None and dff.fit("r", method="wdfmi_nls") is None
+
+
+def test_tunables_snapshot_follows_module_patches(lib):
+    import types
+    from deepfmkit_b200 import fit as tun
+    old = tun.FITOK_THRESHOLD
+    try:
+        tun.FITOK_THRESHOLD = 5e-4
+        assert tun.current_lm_opts().fitok_threshold == 5e-4
+    finally:
+        tun.FITOK_THRESHOLD = old
+    ref_like = types.SimpleNamespace(MAX_LMA_STEPS=7, M_GRID_STEP=0.25)  # a patched reference fit module
+    o = tun.current_lm_opts(ref_like)
+    assert o.max_lma_steps == 7 and o.m_grid_step == 0.25 and o.fitok_threshold == 1e-3
+
+
+def test_slab_bounds_cover_and_balance():
+    from deepfmkit_b200.sharding import all_slab_bounds, slab_bounds
+    for n, w in ((180000, 8), (7, 3), (2, 4), (0, 2), (12800001, 8)):
+        b = all_slab_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        slab_bounds(10, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from deepfmkit_b200.sharding import slab_bounds, gather_rows, broadcast_seed
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+nbuf = 11
+lo, hi = slab_bounds(nbuf, world, rank)
+seed = broadcast_seed([1.0, 6.0, 0.25, -0.5] if rank == 0 else [0, 0, 0, 0])
+assert list(seed) == [1.0, 6.0, 0.25, -0.5]
+rows = np.zeros((hi - lo, 8))
+rows[:, 0] = np.arange(lo, hi)      # stand-in for the per-slab fit: row index ...
+rows[:, 1] = seed[1] + rank         # ... and something that depends on the seed and the rank
+table = gather_rows(rows, nbuf)
+if rank == 0:
+    assert table.shape == (nbuf, 8)
+    assert np.array_equal(table[:, 0], np.arange(nbuf))
+    assert np.array_equal(table[:, 1], np.where(np.arange(nbuf) < 6, 6.0, 7.0))
+    print("GLOO_OK")
+else:
+    assert table is None
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "GLOO_OK" in out.stdout
+
+
+def test_bench_reference_arm_contract():
+    """bench.py's CPU pieces: the sample generator and the pool schedule agree with the sequential oracle."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import dfmi_oracle as orc
+    x = bench.cpu_sample(6, seed=1)
+    assert len(x) == 6 * bench.R
+    rows = orc.nls_fit_pool(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, n_procs=2)
+    ref = orc.nls_fit(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, schedule="seeded", n_chunks=2)
+    assert np.array_equal(rows, ref)
+    assert bench.NBUF == 180000 and bench.R == 20000

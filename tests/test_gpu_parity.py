@@ -1,0 +1,366 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Gates (BASELINE.json north_star): demodulated I/Q within 1e-12 of the buffer's max |I/Q| (fp64);
+m and amp within 1e-8 relative, phi and psi within 1e-8 rad on rows the reference fits (fitok 0/1);
+identical fitok flags everywhere.  EKF states within 1e-9 absolute of the reference loop.
+"""
+import numpy as np
+import pytest
+
+from oracle import dfmi_oracle as orc
+from tests.test_oracle_golden import _signal_from_meta, ekf_kwargs
+
+pytestmark = pytest.mark.gpu
+
+IQ_TOL = 1e-12
+PARAM_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch_mod):
+    from deepfmkit_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _case(golden, name):
+    g = golden(name)
+    meta = g["meta"]
+    x = g["x"] if "x" in g.files else _signal_from_meta(meta)
+    f_samp, f_mod, n, nh = meta[1], meta[2], int(meta[8]), int(meta[9])
+    R = int(f_samp / f_mod * n)
+    return g, x, f_samp, f_mod, n, nh, R, orc.rad_per_sample(f_samp, f_mod)
+
+
+def gpu_demod(torch, ctx, x, R, nh, w0):
+    nbuf = len(x) // R
+    xd = torch.from_numpy(np.ascontiguousarray(x[: nbuf * R])).cuda()
+    qi = torch.empty((nbuf, 2 * nh), dtype=torch.float64, device="cuda")
+    dc = torch.empty(nbuf, dtype=torch.float64, device="cuda")
+    ctx.demod(xd.data_ptr(), nbuf, R, nh, w0, qi.data_ptr(), dc.data_ptr())
+    ctx.synchronize()
+    return qi.cpu().numpy(), dc.cpu().numpy()
+
+
+def assert_rows_match(rows, ref, tol=PARAM_TOL):
+    assert np.array_equal(rows[:, 6], ref[:, 6]), (rows[:, 6], ref[:, 6])
+    ok = ref[:, 6] < 2
+    assert np.all(np.abs(rows[ok, 0] - ref[ok, 0]) <= tol * np.abs(ref[ok, 0]))
+    assert np.all(np.abs(rows[ok, 1] - ref[ok, 1]) <= tol * np.abs(ref[ok, 1]))
+    assert np.all(np.abs(rows[ok, 2] - ref[ok, 2]) <= tol)
+    assert np.all(np.abs(rows[ok, 3] - ref[ok, 3]) <= tol)
+    assert np.all(np.abs(rows[ok, 5] - ref[ok, 5]) <= 1e-8 * np.maximum(ref[ok, 5], 1e-12))
+    assert np.all(np.abs(rows[:, 4] - ref[:, 4]) <= 1e-14 * np.abs(ref[:, 4]))  # dc
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_bessel_device_vs_scipy(torch_mod, ctx, golden):
+    g = golden("bessel_jv")
+    xs = torch_mod.from_numpy(g["xs"]).cuda()
+    out = torch_mod.empty((len(g["xs"]), 66), dtype=torch_mod.float64, device="cuda")
+    ctx.bessel_dev(xs.data_ptr(), len(g["xs"]), 65, out.data_ptr())
+    ctx.synchronize()
+    err = np.abs(out.cpu().numpy() - g["jv"]).max(axis=1)
+    small = np.abs(g["xs"]) <= 200
+    assert err[small].max() < 2.5e-15 and err[~small].max() < 1e-14
+
+
+@pytest.mark.parametrize("name", ["cfg1_quickstart", "cfg2_1mhz", "cfg3_channel", "deep_mod_n62", "fallback_m16",
+                                  "pathological_m3", "low_snr"])
+def test_demod_folded_vs_reference(torch_mod, ctx, golden, name):
+    from deepfmkit_b200 import _lib
+    g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, name)
+    assert _lib.demod_path(R, w0) == 1
+    qi, dc = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    ref = g["qi"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(qi - ref) / scale) <= IQ_TOL, np.max(np.abs(qi - ref) / scale)
+    assert np.all(np.abs(dc - g["rows_seq"][:, 4]) <= 1e-14 * np.abs(g["rows_seq"][:, 4]))
+
+
+@pytest.mark.parametrize("f_samp,f_mod,n,nh", [(200e3, 1234.5, 20, 10), (201e3, 1000.0, 20, 10), (48e3, 440.0, 7, 13),
+                                               (200e3, 1000.0, 1, 15)])
+def test_demod_vs_oracle_general(torch_mod, ctx, f_samp, f_mod, n, nh):
+    """Non-integer / odd periods go through the direct kernel; n = 1 (cfg 5) through the folded one."""
+    x = orc.snr_signal(6.0, f_samp, f_mod, 0.05, 40.0, seed=3)
+    R, _, nbuf = orc.buffer_geometry(len(x), f_samp, f_mod, n)
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    qi, dc = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    for b in list(range(min(nbuf, 6))) + [nbuf - 1]:
+        buf = x[b * R:(b + 1) * R]
+        ref = orc.lockin_means(buf, w0, nh)
+        assert np.max(np.abs(qi[b] - ref)) <= IQ_TOL * np.abs(ref).max()
+        assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
+
+
+def test_demod_unaligned_pointer_takes_direct_path(torch_mod, ctx, golden):
+    g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, "cfg1_quickstart")
+    nbuf = len(x) // R
+    xd = torch_mod.zeros(len(x) + 1, dtype=torch_mod.float64, device="cuda")
+    xd[1:] = torch_mod.from_numpy(x).cuda()
+    qi = torch_mod.empty((nbuf, 2 * nh), dtype=torch_mod.float64, device="cuda")
+    dc = torch_mod.empty(nbuf, dtype=torch_mod.float64, device="cuda")
+    ctx.demod(xd.data_ptr() + 8, nbuf, R, nh, w0, qi.data_ptr(), dc.data_ptr())
+    ctx.synchronize()
+    ref = g["qi"]
+    assert np.max(np.abs(qi.cpu().numpy() - ref) / np.abs(ref).max(axis=1, keepdims=True)) <= IQ_TOL
+
+
+@pytest.mark.parametrize("lanes", [0, 1, 4, 32])
+@pytest.mark.parametrize("name", ["cfg1_quickstart", "cfg2_1mhz", "cfg3_channel", "deep_mod_n62", "fallback_m16",
+                                  "pathological_m3", "low_snr"])
+def test_nls_rows_vs_reference(torch_mod, ctx, golden, name, lanes):
+    from deepfmkit_b200 import _lib
+    g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, name)
+    meta = g["meta"]
+    opts = _lib.default_lm_opts()
+    opts.lanes_per_fit = lanes
+    rows = ctx.nls_fit_host(x, R, nh, w0, [meta[11], meta[12], 0.0, meta[13]], seeded=True, opts=opts)
+    assert_rows_match(rows, g["rows_seq"])
+    if len(g["rows_par"]):
+        assert_rows_match(rows, g["rows_par"])
+
+
+def test_lm_fit_on_reference_harmonic_vectors(torch_mod, ctx, golden):
+    """dfk_lm_fit alone, fed the reference's own I/Q means: isolates the solver from the demodulation."""
+    g = golden("solver_units")
+    nh = int(g["nh"])
+    for key, st_key, p_key in (("clean_qi", "clean_status", "clean_p"), ("data", "fit_status", "fit_p")):
+        qi = torch_mod.from_numpy(g[key]).cuda()
+        nfit = qi.shape[0]
+        guess = torch_mod.tensor([1.6, 6.0, 0.0, 0.0], dtype=torch_mod.float64, device="cuda")
+        rows = torch_mod.zeros((nfit, 8), dtype=torch_mod.float64, device="cuda")
+        ctx.lm_fit(qi.data_ptr(), nfit, nh, guess.data_ptr(), 0, None, None, rows.data_ptr())
+        ctx.synchronize()
+        rows = rows.cpu().numpy()
+        assert np.array_equal(rows[:, 6], g[st_key])
+        ok = g[st_key] < 2
+        ref = g[p_key]
+        assert np.all(np.abs(rows[ok, 0] - ref[ok, 0]) <= PARAM_TOL * np.abs(ref[ok, 0]))
+        assert np.all(np.abs(rows[ok, 1] - ref[ok, 1]) <= PARAM_TOL * np.abs(ref[ok, 1]))
+        assert np.all(np.abs(rows[ok, 2:4] - ref[ok, 2:4]) <= PARAM_TOL)
+
+
+def test_cfg5_batch_per_channel_guess(torch_mod, golden):
+    """CRLB sweep recipe: one period per realisation, N = 15, init_m = m_true, all in one launch."""
+    from deepfmkit_b200 import nls_fit_batch
+    g = golden("cfg5_crlb")
+    ms, trials = g["ms"], int(g["trials"])
+    recs, init_m = [], []
+    for m in ms:
+        for t in range(trials):
+            recs.append(orc.snr_signal(float(m), 200e3, 1000, 1 / 1000, 40.0, seed=t))
+            init_m.append(float(m))
+    rows = nls_fit_batch(np.stack(recs), 200e3, 1000.0, 1, ndata=15, init_m=np.array(init_m), seeded=False)
+    ref = g["rows"].reshape(-1, 7)
+    assert_rows_match(rows[:, 0, :], ref)
+
+
+def test_multichannel_batch_matches_per_channel_calls(torch_mod, ctx):
+    from deepfmkit_b200 import nls_fit_batch
+    chans = [orc.snr_signal(6.0, 200e3, 1000, 0.2, 40.0, seed=c, phi0=2 * np.pi * c / 5) for c in range(5)]
+    rows = nls_fit_batch(np.stack(chans), 200e3, 1000.0, 20)
+    w0 = orc.rad_per_sample(200e3, 1000.0)
+    for c, x in enumerate(chans):
+        single = ctx.nls_fit_host(x, 4000, 10, w0, [1.6, 6.0, 0.0, 0.0], seeded=True)
+        assert np.array_equal(single, rows[c])
+    ref = orc.nls_fit(chans[3], 200e3, 1000.0, 20, 10, schedule="gpu")
+    assert_rows_match(rows[3], ref)
+
+
+def test_host_entry_streams_slabs(torch_mod, ctx):
+    """A record longer than one 128 MiB slab: rows must not depend on where the slab boundaries fall."""
+    from deepfmkit_b200 import _lib
+    R, nh = 4000, 10
+    w0 = orc.rad_per_sample(200e3, 1000.0)
+    nbuf = 9000  # 288 MB
+    xd = torch_mod.empty(nbuf * R, dtype=torch_mod.float64, device="cuda")
+    ctx.synth_snr_dev(xd.data_ptr(), nbuf * R, 1, 200e3, 1000.0, 6.0, snr_db=40.0, seed=5)
+    ctx.synchronize()
+    x = xd.cpu().numpy()
+    rows = ctx.nls_fit_host(x, R, nh, w0, [1.6, 6.0, 0.0, 0.0], seeded=True)
+    rows_dev = torch_mod.empty((nbuf, 8), dtype=torch_mod.float64, device="cuda")
+    ctx.nls_fit_dev(xd.data_ptr(), nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0], True, None, rows_dev.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(rows, rows_dev.cpu().numpy())
+    assert np.all(rows[:, 6] == 0)
+    for b in (0, 1, 4194, 4195, 8999):  # around the slab boundary (128 MiB / 32 kB = 4194.3 buffers)
+        ref = orc.nls_fit(x[b * R:(b + 1) * R], 200e3, 1000.0, 20, nh,
+                          init_a=rows[0, 0] if b else 1.6, init_m=rows[0, 1] if b else 6.0,
+                          init_psi=rows[0, 3] if b else 0.0)
+        # the oracle cold-starts phi at 0 while the GPU seeds it from buffer 0: same minimum, 1e-8 gate
+        assert_rows_match(rows[b:b + 1], ref)
+
+
+@pytest.mark.parametrize("name", ["ekf_default", "ekf_offset"])
+def test_ekf_vs_reference(torch_mod, ctx, golden, name):
+    from deepfmkit_b200 import _lib
+    g = golden(name)
+    kw = ekf_kwargs(g)
+    opts = _lib.default_ekf_opts()
+    for i, key in enumerate(("init_a", "init_m", "init_phi", "init_psi")):
+        if key in kw:
+            opts.init[i] = kw[key]
+    for i in range(5):
+        if "p0_diag" in kw:
+            opts.p0_diag[i] = kw["p0_diag"][i]
+        if "q_diag" in kw:
+            opts.q_diag[i] = kw["q_diag"][i]
+    if "r_val" in kw:
+        opts.r_val = kw["r_val"]
+    rows = ctx.ekf_host(g["x"][None, :], 4000, 200e3, 1000.0, opts)[0]
+    ref = g["rows"]
+    assert np.max(np.abs(rows[:, :5] - ref[:, :5])) < 1e-9
+    assert np.all(rows[:, 5] == 0) and np.all(rows[:, 6] == 1)
+
+
+def test_ekf_batch_layouts_agree(torch_mod, golden):
+    from deepfmkit_b200 import ekf_fit_batch
+    g = golden("ekf_default")
+    x = g["x"][:20000]
+    z = np.stack([x, x[::-1].copy(), x * 1.01])
+    a = ekf_fit_batch(z, 200e3, 1000.0, 20)
+    b = ekf_fit_batch(np.ascontiguousarray(z.T), 200e3, 1000.0, 20, time_major=True)
+    assert np.array_equal(a, b)
+    ref = orc.ekf_track(x, 200e3, 1000.0, 20)
+    assert np.max(np.abs(a[0, :, :5] - ref[:, :5])) < 1e-9
+
+
+# ---- the reference-facing Python API --------------------------------------------------------------
+def test_fitter_api_and_result_frame(torch_mod, golden):
+    import pandas as pd
+    from deepfmkit_b200 import DeepFitFramework, DeepRawObject, StandardNLSFitter
+    g = golden("facade_quickstart")
+    x = orc.snr_signal(6.0, 200e3, 1000, 1, 40.0, seed=0)
+    raw = DeepRawObject(data=pd.DataFrame(x, columns=["ch0"]), f_samp=200e3, f_mod=1000, label="dynamic_channel")
+    df = StandardNLSFitter({"n": 20}).fit(raw, parallel=True, n_cores=3)
+    assert list(df.columns) == list(g["columns"][:7])
+    assert [str(t) for t in df.dtypes] == list(g["dtypes"][:7])
+    assert_rows_match(df.to_numpy(dtype=float), g["values"][:, :7])
+
+    class _Laser:
+        df = float(g["laser_df"])
+
+    class _Sim:
+        label = "dynamic_channel"
+        laser = _Laser()
+        fit_n = 20
+
+    raw.sim = _Sim()
+    dff = DeepFitFramework()
+    dff.load_raw_object(raw)
+    dff.sims["dynamic_channel"] = raw.sim
+    fobj = dff.fit("dynamic_channel", parallel=False)
+    out = dff.fits_df["dynamic_channel_nls"]
+    assert list(out.columns) == list(g["columns"])
+    assert [str(t) for t in out.dtypes] == list(g["dtypes"])
+    assert np.allclose(out["tau"].to_numpy(), g["values"][:, 7], rtol=1e-8, atol=0)
+    assert np.array_equal(fobj.time, g["time"])
+    assert [fobj.n, fobj.R, fobj.fs, fobj.nbuf, fobj.ndata, fobj.init_a, fobj.init_m, fobj.f_samp, fobj.f_mod] == \
+        list(g["scalars"])
+    assert dff.fit("nope") is None and dff.fit("dynamic_channel", method="bogus") is None
+
+
+def test_fitter_edge_cases(torch_mod):
+    import pandas as pd
+    from deepfmkit_b200 import DeepRawObject, EKFFitter, StandardNLSFitter
+    with pytest.raises(ValueError):
+        StandardNLSFitter({})
+    short = DeepRawObject(data=np.ones(100), f_samp=200e3, f_mod=1000)
+    assert StandardNLSFitter({"n": 20}).fit(short).empty  # nbuf == 0 -> empty frame (fitters.py:363)
+    x = orc.snr_signal(6.0, 200e3, 1000, 0.0417, 40.0, seed=2)  # ragged tail: 2 buffers + 340 samples
+    raw = DeepRawObject(data=x, f_samp=200e3, f_mod=1000)
+    df = StandardNLSFitter({"n": 20, "ndata": 12}).fit(raw, init_m=6.2)
+    assert len(df) == 2 and set(df["fitok"]) == {0}
+    before = raw.data.to_numpy().copy()
+    e = EKFFitter({"n": 20}).fit(raw, verbose=False)
+    assert len(e) == 2 and list(e.columns) == ["amp", "m", "phi", "psi", "dc", "ssq", "fitok"]
+    assert e["fitok"].dtype == np.int64 and set(e["fitok"]) == {1}
+    assert np.array_equal(raw.data.to_numpy(), before)  # caller's record untouched
+
+
+def test_tunables_are_read_at_call_time(torch_mod, golden):
+    from deepfmkit_b200 import DeepRawObject, StandardNLSFitter
+    from deepfmkit_b200 import fit as tun
+    g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, "fallback_m16")
+    raw = DeepRawObject(data=x, f_samp=f_samp, f_mod=f_mod)
+    base = StandardNLSFitter({"n": n, "ndata": nh}).fit(raw)
+    assert 1 in set(base["fitok"])
+    old = tun.M_GRID_MAX
+    try:
+        tun.M_GRID_MAX = 10.0  # the grid no longer reaches m = 16: buffer 0 stays unfitted
+        patched = StandardNLSFitter({"n": n, "ndata": nh}).fit(raw)
+    finally:
+        tun.M_GRID_MAX = old
+    ref = orc.nls_fit(x, f_samp, f_mod, n, nh, schedule="gpu", tun=orc.with_tunables(m_grid_max=10.0))
+    assert np.array_equal(patched["fitok"].to_numpy(), ref[:, 6].astype(np.int64))
+    assert patched["fitok"].iloc[0] == 2
+
+
+# ---- full-size properties (BASELINE configs at scale, no oracle possible) -------------------------------
+def test_large_record_properties(torch_mod, ctx):
+    """cfg 2 geometry (1 MHz, R = 20000) on a 1.6 GB device-generated record: linearity of the lock-in,
+    agreement of the two demod kernels, and fits that recover the generating parameters."""
+    torch = torch_mod
+    R, nh, nbuf = 20000, 10, 10000
+    w0 = orc.rad_per_sample(1e6, 1000.0)
+    x = torch.empty(nbuf * R, dtype=torch.float64, device="cuda")
+    ctx.synth_snr_dev(x.data_ptr(), nbuf * R, 1, 1e6, 1000.0, 6.0, snr_db=40.0, seed=11)
+    qi = torch.empty((nbuf, 2 * nh), dtype=torch.float64, device="cuda")
+    dc = torch.empty(nbuf, dtype=torch.float64, device="cuda")
+    ctx.demod(x.data_ptr(), nbuf, R, nh, w0, qi.data_ptr(), dc.data_ptr())
+    ctx.synchronize()
+    # direct kernel on a misaligned copy of the first 64 buffers
+    y = torch.empty(64 * R + 1, dtype=torch.float64, device="cuda")
+    y[1:] = x[: 64 * R]
+    qi2 = torch.empty((64, 2 * nh), dtype=torch.float64, device="cuda")
+    dc2 = torch.empty(64, dtype=torch.float64, device="cuda")
+    ctx.demod(y.data_ptr() + 8, 64, R, nh, w0, qi2.data_ptr(), dc2.data_ptr())
+    ctx.synchronize()
+    scale = qi[:64].abs().max(dim=1, keepdim=True).values
+    assert float(((qi[:64] - qi2).abs() / scale).max()) <= IQ_TOL
+    # linearity: demod(2x + 1) = 2 demod(x) (harmonics reject the constant), dc -> 2 dc + 1
+    z = x[: 256 * R] * 2.0 + 1.0
+    qi3 = torch.empty((256, 2 * nh), dtype=torch.float64, device="cuda")
+    dc3 = torch.empty(256, dtype=torch.float64, device="cuda")
+    ctx.demod(z.data_ptr(), 256, R, nh, w0, qi3.data_ptr(), dc3.data_ptr())
+    ctx.synchronize()
+    assert float((qi3 - 2 * qi[:256]).abs().max()) < 1e-13
+    assert float((dc3 - (2 * dc[:256] + 1)).abs().max()) < 1e-13
+    # whole readout
+    rows = torch.empty((nbuf, 8), dtype=torch.float64, device="cuda")
+    ctx.nls_fit_dev(x.data_ptr(), nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0], True, None, rows.data_ptr())
+    ctx.synchronize()
+    r = rows.cpu().numpy()
+    assert np.all(r[:, 6] == 0)
+    assert abs(r[:, 1].mean() - 6.0) < 1e-4 and r[:, 1].std() < 2e-3
+    assert abs(r[:, 0].mean() - 1.0) < 1e-4 and abs(r[:, 2].mean()) < 1e-3
+
+
+def test_synth_statistics(torch_mod, ctx):
+    torch = torch_mod
+    T = 4_000_000
+    x = torch.empty(2 * T, dtype=torch.float64, device="cuda")
+    ctx.synth_snr_dev(x.data_ptr(), T, 2, 200e3, 1000.0, 6.0, phi0=0.3, dphi=0.5, snr_db=20.0, seed=9)
+    ctx.synchronize()
+    for c in range(2):
+        clean = orc.snr_signal(6.0, 200e3, 1000.0, 0.05, 300.0, seed=0, phi0=0.3 + 0.5 * c)  # 300 dB = noise free
+        xc = x[c * T:(c + 1) * T].cpu().numpy()
+        noise = xc[: len(clean)] - clean
+        full_noise = xc - np.tile(clean[:200], T // 200)
+        sigma = np.sqrt(np.mean((clean - clean.mean()) ** 2) / 100.0)
+        assert abs(full_noise.mean()) < 5 * sigma / np.sqrt(T)
+        assert abs(full_noise.std() / sigma - 1) < 5e-3
+        assert abs(np.corrcoef(full_noise[:-1], full_noise[1:])[0, 1]) < 5e-3
+        assert np.abs(noise).max() < 7 * sigma
+    a = x[:T].cpu().numpy()
+    b = x[T:].cpu().numpy()
+    assert abs(np.corrcoef(a - a.mean(), b - b.mean())[0, 1]) < 0.9  # different seeds per channel
