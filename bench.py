@@ -244,10 +244,10 @@ def run_gpu(args):
 
     # ---- end to end through the host-pointer entry (what StandardNLSFitter.fit calls) ----------------------
     import psutil
-    rec_bytes = NBUF * R * 8
-    avail = psutil.virtual_memory().available
+    # every rank pins its own host copy; keep the sum under 45% of the box's RAM (same answer on every rank)
+    host_total = psutil.virtual_memory().total
     e2e_nbuf = NBUF
-    while e2e_nbuf * R * 8 * world > 0.5 * avail and e2e_nbuf > 1000:
+    while e2e_nbuf * R * 8 * world > 0.45 * host_total and e2e_nbuf > 1000:
         e2e_nbuf //= 2
     xh = torch.empty(e2e_nbuf * R, dtype=torch.float64, pin_memory=True)
     xh.copy_(x[: e2e_nbuf * R])

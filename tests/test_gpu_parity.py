@@ -70,7 +70,8 @@ def test_bessel_device_vs_scipy(torch_mod, ctx, golden):
     ctx.synchronize()
     err = np.abs(out.cpu().numpy() - g["jv"]).max(axis=1)
     small = np.abs(g["xs"]) <= 200
-    assert err[small].max() < 2.5e-15 and err[~small].max() < 1e-14
+    # |x| > 200 starts the upward recurrence from CUDA's j0/j1 (documented abs error ~1e-12 there)
+    assert err[small].max() < 2.5e-15 and err[~small].max() < 2e-12
 
 
 @pytest.mark.parametrize("name", ["cfg1_quickstart", "cfg2_1mhz", "cfg3_channel", "deep_mod_n62", "fallback_m16",
