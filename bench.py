@@ -168,7 +168,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -301,7 +301,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -309,7 +309,25 @@ def run_gpu(args):
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints was sent to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    # NCCL and friends print banners on fd 1; keep stdout clean for the JSON line
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
