@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -139,6 +140,11 @@ struct Guard {  // make the context's device current for the duration of a call
     Guard guard_(ctx);                                             \
     if (!guard_.ok) return fail(DFK_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
 
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : fallback;
+}
+
 dfk::LmOpts to_opts(const dfk_lm_opts* o) {
     dfk_lm_opts d;
     if (!o) {
@@ -167,33 +173,67 @@ struct FoldGeometry {
 
 bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeometry* g) {
     const int P = static_cast<int>(pl.P);
-    int pps = dfk::kFoldStageBytes / (P * 8);
+    // development overrides (tuning runs only): DFK_FOLD_STAGE_BYTES, DFK_FOLD_NSTAGES, DFK_FOLD_CTAS
+    const int env_stage = env_int("DFK_FOLD_STAGE_BYTES", 0), env_nst = env_int("DFK_FOLD_NSTAGES", 0),
+              env_ctas = env_int("DFK_FOLD_CTAS", 0);
+    int pps = (env_stage > 0 ? env_stage : dfk::kFoldStageBytes) / (P * 8);
     if (pps < 1) pps = 1;
     if (pps > pl.periods) pps = static_cast<int>(pl.periods);
-    // prefer two resident CTAs per SM (one folds while the other takes harmonics) with a ring of
-    // 3..6 stages; fall back to one CTA per SM with whatever ring fits
+    if (env_nst > 0 || env_ctas > 0) {
+        const int ctas = env_ctas > 0 ? env_ctas : 2, nst = env_nst > 0 ? env_nst : 4;
+        const dfk::FoldSmem L = dfk::fold_smem_layout(P, pps, nst, N, pl.drift);
+        if (L.total <= static_cast<size_t>(ctx->max_smem_optin) &&
+            static_cast<size_t>(ctas) * (L.total + 1024) <= static_cast<size_t>(ctx->smem_per_sm)) {
+            g->pps = pps;
+            g->nstages = nst;
+            g->smem = L.total;
+            g->ctas_per_sm = ctas;
+            return true;
+        }
+        return false;  // the override does not fit: take the direct kernel rather than mislead a sweep
+    }
+    // Measured on B200 (profiles/r01_tune_demod_*.jsonl): throughput follows the bytes in flight per SM and
+    // prefers few large stages (fewer mbarrier round trips), saturating near 7.3 TB/s from ~130 kB up.
+    // Candidates: 1 or 2 resident CTAs, stages of 16..64 kB of whole periods, rings of 2..6 stages; take the
+    // most bytes in flight, then the larger stage, then two CTAs (one folds while the other takes harmonics).
+    const int stage_targets[] = {65536, 40960, 32768, 24576, 16384};
+    size_t best_flight = 0;
+    int best_stage = 0;
+    bool found = false;
     for (int ctas = 2; ctas >= 1; --ctas) {
         const size_t budget = ctas == 2 ? static_cast<size_t>(ctx->smem_per_sm) / 2 - 1024
                                         : static_cast<size_t>(ctx->max_smem_optin);
-        for (int nst = 6; nst >= (ctas == 2 ? 3 : 2); --nst) {
-            const dfk::FoldSmem L = dfk::fold_smem_layout(P, pps, nst, N, pl.drift);
-            if (L.total <= budget) {
-                g->pps = pps;
-                g->nstages = nst;
-                g->smem = L.total;
-                g->ctas_per_sm = ctas;
-                return true;
+        for (int target : stage_targets) {
+            int q = target / (P * 8);
+            if (q < 1) q = 1;
+            if (q > pl.periods) q = static_cast<int>(pl.periods);
+            for (int nst = 6; nst >= 2; --nst) {
+                const dfk::FoldSmem L = dfk::fold_smem_layout(P, q, nst, N, pl.drift);
+                if (L.total > budget) continue;
+                const int stage_bytes = q * P * 8;
+                const size_t flight = static_cast<size_t>(ctas) * nst * stage_bytes;
+                if (!found || flight > best_flight || (flight == best_flight && stage_bytes > best_stage)) {
+                    found = true;
+                    best_flight = flight;
+                    best_stage = stage_bytes;
+                    g->pps = q;
+                    g->nstages = nst;
+                    g->smem = L.total;
+                    g->ctas_per_sm = ctas;
+                }
+                break;  // deeper rings of this shape fit less
             }
         }
     }
-    return false;
+    return found;
 }
 
-// nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
 int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
                  double* qi, double* dc, cudaStream_t st) {
     if (nbuf == 0) return DFK_OK;
-    const dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
+    dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
+    const int env_drift = env_int("DFK_FOLD_DRIFT", -1);  // development override
+    if (env_drift >= 0) pl.drift = env_drift != 0;
     FoldGeometry g;
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
     if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, &g)) {
@@ -243,19 +283,29 @@ int pick_lanes(const dfk_ctx* ctx, int64_t nfit, int N, int requested) {
     return g;
 }
 
-template <int G>
-int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
+template <int G, int MINB>
+int launch_first_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
                  const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
-    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     const int64_t fits_per_block = dfk::kLmThreads / G;
     const int64_t blocks = (nfit + fits_per_block - 1) / fits_per_block;
     const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * 16));
-    dfk::lm_first_kernel<G><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
+    dfk::lm_first_kernel<G, MINB><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
+}
+
+template <int G>
+int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
+                 const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+    switch (env_int("DFK_LM_MINB", 4)) {  // development override: resident blocks per SM the kernel is compiled for
+        case 6: return launch_first_b<G, 6>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 8: return launch_first_b<G, 8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        default: return launch_first_b<G, 4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+    }
 }
 
 int ensure_counters(dfk_ctx* ctx) {

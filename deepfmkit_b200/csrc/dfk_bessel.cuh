@@ -10,6 +10,7 @@
 
 namespace dfk {
 
+constexpr double kBesselNoRescaleAbove = 1.0e-2;
 constexpr double kBesselForwardAbove = 200.0;  // beyond this |x| > every supported order: go upward from J0, J1
 
 // Starting order for the downward recurrence.  The truncation error of Miller's scheme is ~J_M(x), so M
@@ -54,18 +55,39 @@ DFK_HD int bessel_j_upto(double x, int nmax, double* out, int stride) {
         double bp = 0.0;      // b_{k+1}
         double b = 1.0e-200;  // b_k at k = mstart
         double sum = 0.0;     // b_0 + 2 * sum of even orders
-        for (int k = mstart; k >= 1; --k) {
-            // here b = b_k, bp = b_{k+1}
-            if (k <= nmax) out[k * stride] = b;
-            if ((k & 1) == 0) sum += 2.0 * b;
-            const double bm = static_cast<double>(k) * tox * b - bp;  // b_{k-1}
-            bp = b;
-            b = bm;
-            if (fabs(b) > 1.0e200) {  // keep the unnormalised sequence in range (tiny |x|)
-                b *= 1.0e-200;
-                bp *= 1.0e-200;
-                sum *= 1.0e-200;
-                for (int q = k; q <= nmax; ++q) out[q * stride] *= 1.0e-200;
+        if (ax >= kBesselNoRescaleAbove) {
+            // The unnormalised sequence ends near 1e-200 / |J_mstart(x)|; with mstart <= 70 that stays below
+            // 1e130 for every |x| >= 1e-2, so the loop needs no range check.  mstart is even: two orders per trip.
+            double kd = static_cast<double>(mstart);
+            double even = 0.0;
+            for (int k = mstart; k >= 2; k -= 2) {
+                if (k <= nmax) out[k * stride] = b;
+                even += b;
+                double bm = (kd * tox) * b - bp;  // b_{k-1}
+                bp = b;
+                b = bm;
+                kd -= 1.0;
+                if (k - 1 <= nmax) out[(k - 1) * stride] = b;
+                bm = (kd * tox) * b - bp;  // b_{k-2}
+                bp = b;
+                b = bm;
+                kd -= 1.0;
+            }
+            sum = 2.0 * even;
+        } else {
+            for (int k = mstart; k >= 1; --k) {
+                // here b = b_k, bp = b_{k+1}
+                if (k <= nmax) out[k * stride] = b;
+                if ((k & 1) == 0) sum += 2.0 * b;
+                const double bm = static_cast<double>(k) * tox * b - bp;  // b_{k-1}
+                bp = b;
+                b = bm;
+                if (fabs(b) > 1.0e200) {  // keep the unnormalised sequence in range (tiny |x|)
+                    b *= 1.0e-200;
+                    bp *= 1.0e-200;
+                    sum *= 1.0e-200;
+                    for (int q = k; q <= nmax; ++q) out[q * stride] *= 1.0e-200;
+                }
             }
         }
         out[0] = b;

@@ -199,64 +199,76 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
         }
         consumer_bar();
         // symmetric / antisymmetric combinations over j <-> P - j  (j = 0 and j = P/2 pair with nothing)
+        double2* cmb_s = reinterpret_cast<double2*>(sm_cmb);  // (A_j, B_j)   = (S_j + S_{P-j}, S_j - S_{P-j})
+        double2* cmb_u = cmb_s + (half + 1);                  // (AU_j, BU_j) likewise from U
         for (int j = tid; j <= half; j += kFoldConsumers) {
             const bool self = (j == 0) || (j == half);
             const double sa = sm_s[j], sb = self ? 0.0 : sm_s[P - j];
+            cmb_s[j] = make_double2(sa + sb, self ? 0.0 : sa - sb);
             if (DRIFT) {
                 const double ua = sm_u[j], ub = self ? 0.0 : sm_u[P - j];
-                reinterpret_cast<double2*>(sm_cmb)[2 * j] = make_double2(sa + sb, self ? 0.0 : sa - sb);
-                reinterpret_cast<double2*>(sm_cmb)[2 * j + 1] = make_double2(ua + ub, self ? 0.0 : ua - ub);
-            } else {
-                reinterpret_cast<double2*>(sm_cmb)[j] = make_double2(sa + sb, self ? 0.0 : sa - sb);
+                cmb_u[j] = make_double2(ua + ub, self ? 0.0 : ua - ub);
             }
         }
         consumer_bar();
 
-        // harmonic k (k = 0 is the mean) is owned by warp k % 8; lanes stride the half period by 32
+        // harmonic k (k = 0 is the mean) is owned by warp k % 8, two harmonics (k, k + 8) per pass so that
+        // the folded period is read once for both; lanes stride the half period by 32 columns
         const double Rd = static_cast<double>(p.R);
-        for (int k = warp; k <= N; k += kFoldConsumerWarps) {
-            const double2 w0 = sm_tw[k * 32 + lane];
-            const double2 st = sm_step[k];
-            double c = w0.x, s = w0.y;
-            double aq = 0.0, ai = 0.0, aqu = 0.0, aiu = 0.0;
+        for (int k0 = warp; k0 <= N; k0 += 2 * kFoldConsumerWarps) {
+            const int k1 = k0 + kFoldConsumerWarps;
+            const bool two = k1 <= N;
+            const double2 wa = sm_tw[k0 * 32 + lane], sta = sm_step[k0];
+            const double2 wb = two ? sm_tw[k1 * 32 + lane] : make_double2(0.0, 0.0);
+            const double2 stb = two ? sm_step[k1] : make_double2(1.0, 0.0);
+            double ca = wa.x, sa = wa.y, cb = wb.x, sb = wb.y;
+            double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};  // Q, I, Q drift, I drift
             for (int j = lane; j <= half; j += 32) {
+                const double2 ab = cmb_s[j];
+                acc[0][0] = fma(ab.x, ca, acc[0][0]);
+                acc[0][1] = fma(ab.y, sa, acc[0][1]);
+                acc[1][0] = fma(ab.x, cb, acc[1][0]);
+                acc[1][1] = fma(ab.y, sb, acc[1][1]);
                 if (DRIFT) {
-                    const double2 ab = reinterpret_cast<const double2*>(sm_cmb)[2 * j];
-                    const double2 uab = reinterpret_cast<const double2*>(sm_cmb)[2 * j + 1];
-                    aq = fma(ab.x, c, aq);
-                    ai = fma(ab.y, s, ai);
-                    aqu = fma(uab.y, s, aqu);
-                    aiu = fma(uab.x, c, aiu);
-                } else {
-                    const double2 ab = reinterpret_cast<const double2*>(sm_cmb)[j];
-                    aq = fma(ab.x, c, aq);
-                    ai = fma(ab.y, s, ai);
+                    const double2 uab = cmb_u[j];
+                    acc[0][2] = fma(uab.y, sa, acc[0][2]);
+                    acc[0][3] = fma(uab.x, ca, acc[0][3]);
+                    acc[1][2] = fma(uab.y, sb, acc[1][2]);
+                    acc[1][3] = fma(uab.x, cb, acc[1][3]);
                 }
-                const double cn = c * st.x - s * st.y;
-                s = fma(s, st.x, c * st.y);
-                c = cn;
+                const double cna = ca * sta.x - sa * sta.y;
+                sa = fma(sa, sta.x, ca * sta.y);
+                ca = cna;
+                const double cnb = cb * stb.x - sb * stb.y;
+                sb = fma(sb, stb.x, cb * stb.y);
+                cb = cnb;
             }
-            aq = warp_sum(aq);
-            if (k > 0) {
-                ai = warp_sum(ai);
-                if (DRIFT) {
-                    aqu = warp_sum(aqu);
-                    aiu = warp_sum(aiu);
-                }
-            }
-            if (lane == 0) {
-                if (k == 0) {
-                    p.dc[b] = aq / Rd;
-                } else {
-                    double qv = aq, iv = ai;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = h == 0 ? k0 : k1;
+                if (h == 1 && !two) break;
+                double aq = warp_sum(acc[h][0]), ai = 0.0, aqu = 0.0, aiu = 0.0;
+                if (k > 0) {
+                    ai = warp_sum(acc[h][1]);
                     if (DRIFT) {
-                        const double d = p.delta[k - 1];
-                        qv = fma(-d, aqu, qv);
-                        iv = fma(d, aiu, iv);
+                        aqu = warp_sum(acc[h][2]);
+                        aiu = warp_sum(acc[h][3]);
                     }
-                    double* out = p.qi + b * static_cast<long long>(2 * N);
-                    out[k - 1] = qv / Rd;
-                    out[N + k - 1] = iv / Rd;
+                }
+                if (lane == 0) {
+                    if (k == 0) {
+                        p.dc[b] = aq / Rd;
+                    } else {
+                        double qv = aq, iv = ai;
+                        if (DRIFT) {
+                            const double d = p.delta[k - 1];
+                            qv = fma(-d, aqu, qv);
+                            iv = fma(d, aiu, iv);
+                        }
+                        double* out = p.qi + b * static_cast<long long>(2 * N);
+                        out[k - 1] = qv / Rd;
+                        out[N + k - 1] = iv / Rd;
+                    }
                 }
             }
         }

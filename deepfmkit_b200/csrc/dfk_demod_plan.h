@@ -12,6 +12,10 @@
 //     Q_k = (sum_j S_j cos(th_kj) - delta_k sum_j U_j sin(th_kj)) / R
 //     I_k = (sum_j S_j sin(th_kj) + delta_k sum_j U_j cos(th_kj)) / R
 // which brings the result to the reference's own rounding floor (measured 2.5e-14 of max|IQ|).
+// Leaving the term out costs at most ~ramp/2 of max|IQ| (ramp = max_k |delta_k| R; measured 3.5e-14 at
+// ramp = 2.2e-13), so it is only switched on when ramp > kDriftRamp = 4e-13, i.e. before the error could
+// reach 2e-13 -- a fifth of the 1e-12 parity gate.  (Many harmonics or long buffers get there; the
+// BASELINE configs with N = 10 do not.)
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -19,7 +23,8 @@
 namespace dfk {
 
 constexpr int kMaxHarmonics = 64;
-constexpr int64_t kMaxFoldPeriod = 2048;  // 32 lanes x 32 double2 slots
+constexpr int64_t kMaxFoldPeriod = 2048;  // 256 consumer threads x 4 column pairs
+constexpr double kDriftRamp = 4e-13;
 
 struct DemodPlan {
     bool folded;     // integer even period -> folded TMA kernel; else general kernel
@@ -65,7 +70,7 @@ inline DemodPlan make_demod_plan(int64_t R, double w0, int N) {
     pl.folded = true;
     pl.P = P;
     pl.periods = R / P;
-    pl.drift = worst > 3e-14;
+    pl.drift = worst > kDriftRamp;
     return pl;
 }
 

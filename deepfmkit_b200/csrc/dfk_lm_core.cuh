@@ -6,7 +6,7 @@
 // values come from a Miller recurrence kept in a per-lane column, cos/sin(j*psi) come from a
 // rotation recurrence, and the damped 4x4 system is solved in registers by Gaussian elimination
 // with partial pivoting (what np.linalg.solve/LAPACK gesv does, including "exactly singular ->
-// no step", fit.py:197-204).
+// no step", fit.py:197-204) on the block structure the model's Jacobian has (see NormalEq).
 #pragma once
 #include "dfk_bessel.cuh"
 #include "dfk_common.cuh"
@@ -70,10 +70,19 @@ struct Coop {
 };
 
 // ---- normal equations ------------------------------------------------------------------------
+// The model's two rows of harmonic j are  a q_j J_j(m) (cos j psi, -sin j psi)  with q_j = cos(phi + j pi/2).
+// Rotating the data pair (Q_j, I_j) by j psi instead of the model,
+//     u_j = c Q_j - s I_j,   v_j = s Q_j + c I_j      (c, s = cos, sin of j psi),
+// the residual pair becomes (u_j - env_j, v_j) with env_j = a q_j J_j, the amplitude / depth / phase columns
+// of the Jacobian (fit.py:125-140) all point along the first rotated axis and the psi column (fit.py:143-144)
+// along the second.  J^T J is therefore block diagonal -- a 3x3 block and the scalar psi-psi entry; the
+// reference's fourth row/column holds only its rounding noise (~1e-17 of the diagonal) -- and J^T r needs one
+// product per column.  Same numbers as fit.py:68-150 to rounding, about half the arithmetic.
 struct NormalEq {
     double ssq;
-    double a00, a01, a02, a03, a11, a12, a13, a22, a23, a33;  // upper triangle of J^T J
-    double g0, g1, g2, g3;                                    // J^T r
+    double a00, a01, a02, a11, a12, a22;  // amplitude, depth, phase block of J^T J (upper triangle)
+    double a33;                           // psi-psi entry
+    double g0, g1, g2, g3;                // J^T r
 };
 
 // quarter-turn factors: cos(phi + j*pi/2) and its phi-derivative cos(phi + j*pi/2 + pi/2) (fit.py:100,137)
@@ -83,6 +92,19 @@ DFK_HD void quarter_terms(int j, double cphi, double sphi, double& q, double& dq
         case 1: q = -sphi; dq = -cphi; break;
         case 2: q = -cphi; dq = sphi; break;
         default: q = sphi; dq = cphi; break;
+    }
+}
+
+// (q, dq) at harmonic j -> harmonic j + G (G a power of two)
+template <int G>
+DFK_HD void quarter_advance(double& q, double& dq) {
+    if (G == 1) {
+        const double t = q;
+        q = dq;
+        dq = -t;
+    } else if (G == 2) {
+        q = -q;
+        dq = -dq;
     }
 }
 
@@ -102,49 +124,55 @@ DFK_HD void eval_state(int N, const double* qi, int qs, const double* bes, int b
     } else {
         sincos_hd(static_cast<double>(G) * psi, &sg, &cg);
     }
+    double q, dq;
+    quarter_terms(r + 1, cphi, sphi, q, dq);
     NormalEq t = {};
     const double a_on = (a != 0.0) ? 1.0 : 0.0;  // fit.py:126: amplitude column stays zero at a == 0
+    double fj = static_cast<double>(r + 1);
+    const double* qq = qi + r * qs;
+    const double* qv = qi + (N + r) * qs;
+    const double* bb = bes + (r + 1) * bs;
+    double b_lo = bes[r * bs];  // J_{j-1}
     for (int j = r + 1; j <= N; j += G) {
-        double q, dq;
-        quarter_terms(j, cphi, sphi, q, dq);
-        const double B = bes[j * bs];
-        const double dB = 0.5 * (bes[(j - 1) * bs] - bes[(j + 1) * bs]);  // fit.py:108
-        const double fj = static_cast<double>(j);
-        const double shape = q * B;      // model / a
-        const double env = a * shape;    // fit.py:111
-        const double mq = env * c, mi = -env * s;
-        const double rq = qi[(j - 1) * qs] - mq;
-        const double ri = qi[(N + j - 1) * qs] - mi;
-        // Jacobian rows (fit.py:125-144)
-        const double q0 = a_on * shape * c, i0 = -a_on * shape * s;
-        const double dm = a * q * dB;
-        const double q1 = dm * c, i1 = -dm * s;
-        const double dph = a * dq * B;
-        const double q2 = dph * c, i2 = -dph * s;
-        const double q3 = -env * s * fj, i3 = -env * c * fj;
-        t.ssq += rq * rq + ri * ri;
-        t.a00 += q0 * q0 + i0 * i0;
-        t.a01 += q0 * q1 + i0 * i1;
-        t.a02 += q0 * q2 + i0 * i2;
-        t.a03 += q0 * q3 + i0 * i3;
-        t.a11 += q1 * q1 + i1 * i1;
-        t.a12 += q1 * q2 + i1 * i2;
-        t.a13 += q1 * q3 + i1 * i3;
-        t.a22 += q2 * q2 + i2 * i2;
-        t.a23 += q2 * q3 + i2 * i3;
-        t.a33 += q3 * q3 + i3 * i3;
-        t.g0 += q0 * rq + i0 * ri;
-        t.g1 += q1 * rq + i1 * ri;
-        t.g2 += q2 * rq + i2 * ri;
-        t.g3 += q3 * rq + i3 * ri;
+        const double B = bb[0];
+        const double b_hi = bb[bs];
+        const double dB = 0.5 * (b_lo - b_hi);  // fit.py:108
+        const double Qj = qq[0], Ij = qv[0];
+        const double u = c * Qj - s * Ij;  // data rotated by j*psi
+        const double v = s * Qj + c * Ij;
+        const double shape = q * B;
+        const double env = a * shape;  // fit.py:111
+        const double e = u - env;
+        const double x0 = a_on * shape, x1 = (a * q) * dB, x2 = (a * dq) * B, x3 = -(env * fj);
+        t.ssq += e * e + v * v;
+        t.a00 += x0 * x0;
+        t.a01 += x0 * x1;
+        t.a02 += x0 * x2;
+        t.a11 += x1 * x1;
+        t.a12 += x1 * x2;
+        t.a22 += x2 * x2;
+        t.a33 += x3 * x3;
+        t.g0 += x0 * e;
+        t.g1 += x1 * e;
+        t.g2 += x2 * e;
+        t.g3 += x3 * v;
         const double cn = c * cg - s * sg;  // advance cos/sin(j*psi) by G harmonics
         s = s * cg + c * sg;
         c = cn;
+        quarter_advance<G>(q, dq);
+        fj += static_cast<double>(G);
+        qq += G * qs;
+        qv += G * qs;
+        if (G == 1) {
+            b_lo = B;
+        } else if (j + G <= N) {
+            b_lo = bb[(G - 1) * bs];  // J_{j+G-1}; past the last harmonic the column ends
+        }
+        bb += G * bs;
     }
     ne.ssq = Coop<G>::sum(t.ssq);
     ne.a00 = Coop<G>::sum(t.a00); ne.a01 = Coop<G>::sum(t.a01); ne.a02 = Coop<G>::sum(t.a02);
-    ne.a03 = Coop<G>::sum(t.a03); ne.a11 = Coop<G>::sum(t.a11); ne.a12 = Coop<G>::sum(t.a12);
-    ne.a13 = Coop<G>::sum(t.a13); ne.a22 = Coop<G>::sum(t.a22); ne.a23 = Coop<G>::sum(t.a23);
+    ne.a11 = Coop<G>::sum(t.a11); ne.a12 = Coop<G>::sum(t.a12); ne.a22 = Coop<G>::sum(t.a22);
     ne.a33 = Coop<G>::sum(t.a33);
     ne.g0 = Coop<G>::sum(t.g0); ne.g1 = Coop<G>::sum(t.g1); ne.g2 = Coop<G>::sum(t.g2);
     ne.g3 = Coop<G>::sum(t.g3);
@@ -165,35 +193,43 @@ DFK_HD double eval_ssq(int N, const double* qi, int qs, const double* bes, int b
     } else {
         sincos_hd(static_cast<double>(G) * psi, &sg, &cg);
     }
+    double q, dq;
+    quarter_terms(r + 1, cphi, sphi, q, dq);
+    double aq = a * q, adq = a * dq;  // a * cos(phi + j*pi/2) and the next quarter turn
     double acc = 0.0;
+    const double* qq = qi + r * qs;
+    const double* qv = qi + (N + r) * qs;
+    const double* bb = bes + (r + 1) * bs;
     for (int j = r + 1; j <= N; j += G) {
-        double q, dq;
-        quarter_terms(j, cphi, sphi, q, dq);
-        const double env = a * q * bes[j * bs];
-        const double rq = qi[(j - 1) * qs] - env * c;
-        const double ri = qi[(N + j - 1) * qs] + env * s;
-        acc += rq * rq + ri * ri;
+        const double Qj = qq[0], Ij = qv[0];
+        const double e = (c * Qj - s * Ij) - aq * bb[0];
+        const double v = s * Qj + c * Ij;
+        acc += e * e + v * v;
         const double cn = c * cg - s * sg;
         s = s * cg + c * sg;
         c = cn;
+        quarter_advance<G>(aq, adq);
+        qq += G * qs;
+        qv += G * qs;
+        bb += G * bs;
     }
     return Coop<G>::sum(acc);
 }
 
-// (J^T J + lam diag(J^T J)) dp = g by elimination with partial pivoting (fit.py:169-206).
-// Returns false (dp = 0) when a pivot column is exactly zero -- numpy's LinAlgError branch.
+// (J^T J + lam diag(J^T J)) dp = g (fit.py:169-206): elimination with partial pivoting on the 3x3 block, a
+// division for psi.  Returns false (dp = 0) when a pivot is exactly zero -- numpy's LinAlgError branch.
 DFK_HD bool damped_solve(const NormalEq& ne, double lam, double* dp) {
-    double A[4][5] = {{ne.a00 + lam * ne.a00, ne.a01, ne.a02, ne.a03, ne.g0},
-                      {ne.a01, ne.a11 + lam * ne.a11, ne.a12, ne.a13, ne.g1},
-                      {ne.a02, ne.a12, ne.a22 + lam * ne.a22, ne.a23, ne.g2},
-                      {ne.a03, ne.a13, ne.a23, ne.a33 + lam * ne.a33, ne.g3}};
-    bool ok = true;
+    double A[3][4] = {{ne.a00 + lam * ne.a00, ne.a01, ne.a02, ne.g0},
+                      {ne.a01, ne.a11 + lam * ne.a11, ne.a12, ne.g1},
+                      {ne.a02, ne.a12, ne.a22 + lam * ne.a22, ne.g2}};
+    const double d33 = ne.a33 + lam * ne.a33;
+    bool ok = d33 != 0.0;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 3; ++c) {
         int piv = c;
         double best = fabs(A[c][c]);
 #pragma unroll
-        for (int r = c + 1; r < 4; ++r) {
+        for (int r = c + 1; r < 3; ++r) {
             const double v = fabs(A[r][c]);
             if (v > best) {
                 best = v;
@@ -202,10 +238,10 @@ DFK_HD bool damped_solve(const NormalEq& ne, double lam, double* dp) {
         }
         if (!(best > 0.0)) ok = false;
 #pragma unroll
-        for (int r = c + 1; r < 4; ++r) {
+        for (int r = c + 1; r < 3; ++r) {
             if (piv == r) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
+                for (int k = 0; k < 4; ++k) {
                     const double tmp = A[c][k];
                     A[c][k] = A[r][k];
                     A[r][k] = tmp;
@@ -214,21 +250,20 @@ DFK_HD bool damped_solve(const NormalEq& ne, double lam, double* dp) {
         }
         const double inv = 1.0 / A[c][c];
 #pragma unroll
-        for (int r = c + 1; r < 4; ++r) {
+        for (int r = c + 1; r < 3; ++r) {
             const double f = A[r][c] * inv;
 #pragma unroll
-            for (int k = c + 1; k < 5; ++k) A[r][k] -= f * A[c][k];
+            for (int k = c + 1; k < 4; ++k) A[r][k] -= f * A[c][k];
         }
     }
     if (!ok) {
         dp[0] = dp[1] = dp[2] = dp[3] = 0.0;
         return false;
     }
-    const double x3 = A[3][4] / A[3][3];
-    const double x2 = (A[2][4] - A[2][3] * x3) / A[2][2];
-    const double x1 = (A[1][4] - A[1][2] * x2 - A[1][3] * x3) / A[1][1];
-    const double x0 = (A[0][4] - A[0][1] * x1 - A[0][2] * x2 - A[0][3] * x3) / A[0][0];
-    dp[0] = x0; dp[1] = x1; dp[2] = x2; dp[3] = x3;
+    const double x2 = A[2][3] / A[2][2];
+    const double x1 = (A[1][3] - A[1][2] * x2) / A[1][1];
+    const double x0 = (A[0][3] - A[0][1] * x1 - A[0][2] * x2) / A[0][0];
+    dp[0] = x0; dp[1] = x1; dp[2] = x2; dp[3] = ne.g3 / d33;
     return true;
 }
 

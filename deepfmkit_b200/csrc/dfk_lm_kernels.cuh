@@ -51,8 +51,8 @@ DFK_D void flush_counts(const LmCounts& c, LmCounts* global, bool leader) {
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kLmThreads) lm_first_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
+template <int G, int MINB>
+__global__ void __launch_bounds__(kLmThreads, MINB) lm_first_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
                                                               int N, GuessSrc guess, const double* __restrict__ dc,
                                                               LmOpts o, double* rows,
                                                               int* __restrict__ retry_list, int* __restrict__ retry_count,

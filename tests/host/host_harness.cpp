@@ -37,8 +37,9 @@ void hh_eval_state(int N, const double* qi, const double* p, double* out /*1+16+
     NormalEq ne;
     eval_state<1>(N, qi, 1, bes.data(), 1, p, ne);
     out[0] = ne.ssq;
-    const double full[16] = {ne.a00, ne.a01, ne.a02, ne.a03, ne.a01, ne.a11, ne.a12, ne.a13,
-                             ne.a02, ne.a12, ne.a22, ne.a23, ne.a03, ne.a13, ne.a23, ne.a33};
+    // the psi row/column is structurally zero off the diagonal (the reference holds rounding noise there)
+    const double full[16] = {ne.a00, ne.a01, ne.a02, 0.0, ne.a01, ne.a11, ne.a12, 0.0,
+                             ne.a02, ne.a12, ne.a22, 0.0, 0.0, 0.0, 0.0, ne.a33};
     std::memcpy(out + 1, full, sizeof(full));
     out[17] = ne.g0; out[18] = ne.g1; out[19] = ne.g2; out[20] = ne.g3;
 }
@@ -52,9 +53,9 @@ double hh_eval_ssq(int N, const double* qi, const double* p) {
 int hh_solve(const double* jtj16, const double* g, double lam, double* dp) {
     NormalEq ne;
     ne.ssq = 0;
-    ne.a00 = jtj16[0]; ne.a01 = jtj16[1]; ne.a02 = jtj16[2]; ne.a03 = jtj16[3];
-    ne.a11 = jtj16[5]; ne.a12 = jtj16[6]; ne.a13 = jtj16[7];
-    ne.a22 = jtj16[10]; ne.a23 = jtj16[11]; ne.a33 = jtj16[15];
+    ne.a00 = jtj16[0]; ne.a01 = jtj16[1]; ne.a02 = jtj16[2];
+    ne.a11 = jtj16[5]; ne.a12 = jtj16[6];
+    ne.a22 = jtj16[10]; ne.a33 = jtj16[15];
     ne.g0 = g[0]; ne.g1 = g[1]; ne.g2 = g[2]; ne.g3 = g[3];
     return damped_solve(ne, lam, dp) ? 1 : 0;
 }
