@@ -228,6 +228,70 @@ bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeom
     return found;
 }
 
+template <bool DRIFT, int NBW>
+int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid, cudaStream_t st) {
+    DFK_CUDA(cudaFuncSetAttribute(dfk::demod_tile_kernel<DRIFT, NBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    dfk::demod_tile_kernel<DRIFT, NBW><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+    (void)ctx;
+    return DFK_OK;
+}
+
+// Short periods (P <= 256) with contiguous buffers: the barrier-free tile kernel.  Returns 1 if it launched,
+// 0 if the geometry does not fit it, < 0 on error.
+int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int64_t R, int32_t N,
+                    double* qi, double* dc, cudaStream_t st) {
+    if (pl.P > dfk::kTileMaxPeriod || env_int("DFK_NO_TILE", 0)) return 0;
+    const int P = static_cast<int>(pl.P), n = static_cast<int>(pl.periods);
+    int nbw = 8;
+    while (nbw > 1 && static_cast<int64_t>(nbw) * R * 8 > dfk::kTileStageBytes) nbw >>= 1;
+    const int env_nbw = env_int("DFK_TILE_NBW", 0);  // development override
+    if (env_nbw == 1 || env_nbw == 2 || env_nbw == 4 || env_nbw == 8) nbw = env_nbw;
+    int pps = dfk::kTileStageBytes / (P * 8);
+    if (pps < 1) pps = 1;
+    if (pps > nbw * n) pps = nbw * n;
+    int nst = env_int("DFK_TILE_NSTAGES", 12);
+    size_t smem = 0;
+    for (; nst >= 2; --nst) {
+        smem = dfk::tile_smem_layout(P, N, nbw, pps, nst, pl.drift).total;
+        if (smem <= static_cast<size_t>(ctx->max_smem_optin)) break;
+    }
+    if (nst < 2) return 0;
+    dfk::TileParams p;
+    p.x = x;
+    p.qi = qi;
+    p.dc = dc;
+    p.nbuf = nbuf;
+    p.R = static_cast<int>(R);
+    p.P = P;
+    p.periods = n;
+    p.N = N;
+    p.pps = pps;
+    p.cpg = (nbw * n + pps - 1) / pps;
+    p.nstages = nst;
+    for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];
+    const int64_t ngroups = (nbuf + nbw - 1) / nbw;
+    const int grid = static_cast<int>(std::min<int64_t>(ngroups, ctx->sm_count));
+    int rc;
+    if (pl.drift) {
+        switch (nbw) {
+            case 8: rc = launch_tile_t<true, 8>(ctx, p, smem, grid, st); break;
+            case 4: rc = launch_tile_t<true, 4>(ctx, p, smem, grid, st); break;
+            case 2: rc = launch_tile_t<true, 2>(ctx, p, smem, grid, st); break;
+            default: rc = launch_tile_t<true, 1>(ctx, p, smem, grid, st); break;
+        }
+    } else {
+        switch (nbw) {
+            case 8: rc = launch_tile_t<false, 8>(ctx, p, smem, grid, st); break;
+            case 4: rc = launch_tile_t<false, 4>(ctx, p, smem, grid, st); break;
+            case 2: rc = launch_tile_t<false, 2>(ctx, p, smem, grid, st); break;
+            default: rc = launch_tile_t<false, 1>(ctx, p, smem, grid, st); break;
+        }
+    }
+    return rc ? rc : 1;
+}
+
+// nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
 int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
                  double* qi, double* dc, cudaStream_t st) {
     if (nbuf == 0) return DFK_OK;
@@ -236,7 +300,14 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
     if (env_drift >= 0) pl.drift = env_drift != 0;
     FoldGeometry g;
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
-    if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, &g)) {
+    int tiled = 0;
+    if (pl.folded && aligned && ld_c == bpc * R) {
+        tiled = try_launch_tile(ctx, pl, x, nbuf, R, N, qi, dc, st);
+        if (tiled < 0) return tiled;
+    }
+    if (tiled) {
+        // launched above
+    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, &g)) {
         dfk::FoldParams p;
         p.x = x;
         p.qi = qi;

@@ -276,6 +276,284 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
 }
 
 // ---------------------------------------------------------------------------------------------------
+// demod_tile_kernel -- short modulation periods (P <= 256: the 200 kHz configs).  A buffer is then small
+// (32 kB at n = 20, 1.6 kB at n = 1) and the per-buffer block barriers of demod_fold_kernel dominate, so here
+// nothing is synchronised across the CTA: the producer lane streams *groups* of NBW consecutive buffers through
+// one CTA-wide TMA ring, group i of the CTA belongs to warp i % 8 alone, and that warp folds its buffers in
+// registers, forms the j <-> P-j combinations through a private scratch column and takes all 2N+1 outputs of its
+// NBW buffers as one small dense product with a twiddle table held in shared memory for the life of the CTA
+// (lane = output row, NBW accumulators per lane, table value loaded once per NBW buffers).  No recurrence, no
+// shuffles, no __syncthreads after set-up.
+constexpr int kTileMaxPeriod = 256;
+constexpr int kTileMaxSlots = kTileMaxPeriod / 2 / 32;  // column pairs per lane (4)
+constexpr int kTileStageBytes = 16384;
+
+struct TileParams {
+    const double* x;
+    double* qi;
+    double* dc;
+    long long nbuf;
+    int R, P, periods, N;
+    int pps;      // periods per ring stage
+    int cpg;      // stages per full group
+    int nstages;  // ring depth
+    double delta[kMaxHarmonics];
+};
+
+struct TileSmem {
+    int ldt;         // table row stride in doubles (odd: lanes on consecutive rows hit distinct banks)
+    int nv_pad;      // table rows, a multiple of 32
+    int xrow;        // doubles per column j in a warp's operand block
+    int stage_doubles;
+    size_t off_t1, off_t2, off_scr, off_x, off_stage, off_bar, total;
+    size_t scr_per_warp, x_per_warp;  // in doubles
+};
+
+inline __host__ __device__ TileSmem tile_smem_layout(int P, int N, int nbw, int pps, int nstages, bool drift) {
+    TileSmem L;
+    const int half = P / 2;
+    L.ldt = (half + 1) | 1;
+    L.nv_pad = ((2 * N + 1) + 31) / 32 * 32;
+    const int ncomp = drift ? 4 : 2;
+    L.xrow = ncomp * nbw + (nbw > 1 ? 2 : 0);
+    L.stage_doubles = pps * P;
+    L.scr_per_warp = static_cast<size_t>(P) * (drift ? 2 : 1);
+    L.x_per_warp = static_cast<size_t>(half + 1) * L.xrow;
+    size_t o = 0;
+    L.off_stage = o;
+    o += static_cast<size_t>(nstages) * L.stage_doubles * 8;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    L.off_t1 = o;
+    o += static_cast<size_t>(L.nv_pad) * L.ldt * 8;
+    L.off_t2 = o;
+    o += drift ? static_cast<size_t>(L.nv_pad) * L.ldt * 8 : 0;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    L.off_scr = o;
+    o += kFoldConsumerWarps * L.scr_per_warp * 8;
+    o = (o + 15) & ~static_cast<size_t>(15);
+    L.off_x = o;
+    o += kFoldConsumerWarps * ((L.x_per_warp * 8 + 15) & ~static_cast<size_t>(15));
+    L.off_bar = o;
+    o += static_cast<size_t>(2 * nstages + 1) * 8;  // full[], empty[], issued-chunk counter
+    L.total = o;
+    return L;
+}
+
+template <bool DRIFT, int NBW>
+__global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TileSmem L = tile_smem_layout(p.P, p.N, NBW, p.pps, p.nstages, DRIFT);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
+    double* t1 = reinterpret_cast<double*>(smem_raw + L.off_t1);
+    double* t2 = reinterpret_cast<double*>(smem_raw + L.off_t2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* empty = full + p.nstages;
+    // Chunks issued so far.  The warps run independently, so the owner of chunk q + nstages can reach its wait
+    // before chunk q (same stage, opposite parity) has even been issued, and a parity wait cannot tell those two
+    // phases apart; a warp therefore first waits until its chunk has been issued, then on the stage's barrier.
+    volatile unsigned long long* issued = reinterpret_cast<volatile unsigned long long*>(empty + p.nstages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, N = p.N, half = P >> 1, n = p.periods, NV = 2 * N + 1;
+    const long long ngroups = (p.nbuf + NBW - 1) / NBW;
+    // groups of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long long my_groups = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        *issued = 0ull;
+        mbar_fence_init();
+    }
+    // twiddle table: row 0 = 1 (mean), rows 1..N = cos(2 pi k j / P), rows N+1..2N = sin(2 pi k j / P);
+    // second table (drift term): -delta_k sin for the cosine rows, +delta_k cos for the sine rows
+    for (int i = tid; i < L.nv_pad * L.ldt; i += kFoldThreads) {
+        const int v = i / L.ldt, j = i - v * L.ldt;
+        double a = 0.0, b = 0.0;
+        if (v < NV && j <= half) {
+            const int k = v <= N ? v : v - N;
+            double sn, cs;
+            sincospi(2.0 * static_cast<double>((static_cast<long long>(k) * j) % P) / static_cast<double>(P), &sn, &cs);
+            a = v <= N ? cs : sn;
+            if (DRIFT && v > 0) b = v <= N ? -p.delta[k - 1] * sn : p.delta[k - 1] * cs;
+        }
+        t1[i] = a;
+        if (DRIFT) t2[i] = b;
+    }
+    __syncthreads();
+
+    if (warp == kFoldConsumerWarps) {
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int stage = 0;
+            uint32_t phase = 0;
+            unsigned long long count = 0;
+            for (long long i = 0; i < my_groups; ++i) {
+                const long long g = blockIdx.x + i * gridDim.x;
+                const long long b0 = g * NBW;
+                const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+                const int tot = nb * n;  // periods in this group
+                const double* src = p.x + b0 * static_cast<long long>(p.R);
+                for (int q0 = 0; q0 < tot; q0 += p.pps) {
+                    const int np = min(p.pps, tot - q0);
+                    const uint32_t bytes = static_cast<uint32_t>(np) * static_cast<uint32_t>(P) * 8u;
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    bulk_load(stage_base + static_cast<size_t>(stage) * L.stage_doubles,
+                              src + static_cast<size_t>(q0) * P, bytes, &full[stage], pol);
+                    __threadfence_block();
+                    *issued = ++count;
+                    if (++stage == p.nstages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    double* scr_s = reinterpret_cast<double*>(smem_raw + L.off_scr) + warp * L.scr_per_warp;
+    double* scr_u = scr_s + P;
+    double* X = reinterpret_cast<double*>(smem_raw + L.off_x + warp * ((L.x_per_warp * 8 + 15) & ~static_cast<size_t>(15)));
+    const int xrow = L.xrow;
+    const double Rd = static_cast<double>(p.R);
+
+    // Ring position of chunk number q (CTA-wide count): stage q % nstages, phase (q / nstages) & 1.  Full groups
+    // have cpg chunks; only the CTA's last group can be short, so the count before group i is i * cpg.
+    for (long long i = warp; i < my_groups; i += kFoldConsumerWarps) {
+        const long long g = blockIdx.x + i * gridDim.x;
+        const long long b0 = g * NBW;
+        const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+        const int tot = nb * n;
+        long long q = i * p.cpg;
+        double2 accS[kTileMaxSlots], accT[kTileMaxSlots];
+#pragma unroll
+        for (int s = 0; s < kTileMaxSlots; ++s) accS[s] = accT[s] = make_double2(0.0, 0.0);
+        int pin = 0;   // period index inside the current buffer
+        int slot = 0;  // buffer inside the group
+        for (int q0 = 0; q0 < tot; q0 += p.pps, ++q) {
+            const int np = min(p.pps, tot - q0);
+            const int stage = static_cast<int>(q % p.nstages);
+            const uint32_t phase = static_cast<uint32_t>((q / p.nstages) & 1);
+            while (*issued <= static_cast<unsigned long long>(q)) __nanosleep(64);
+            __threadfence_block();
+            mbar_wait(&full[stage], phase);
+            const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+            for (int c = 0; c < np; ++c) {
+                const double2* row = reinterpret_cast<const double2*>(sm + c * P);
+                const double cin = static_cast<double>(pin);
+#pragma unroll
+                for (int s = 0; s < kTileMaxSlots; ++s) {
+                    const int pair = lane + 32 * s;
+                    if (pair < half) {
+                        const double2 v = row[pair];
+                        accS[s].x += v.x;
+                        accS[s].y += v.y;
+                        if (DRIFT) {
+                            accT[s].x = fma(cin, v.x, accT[s].x);
+                            accT[s].y = fma(cin, v.y, accT[s].y);
+                        }
+                    }
+                }
+                if (++pin == n) {
+                    // buffer complete: folded period -> scratch -> even/odd combinations -> operand block
+#pragma unroll
+                    for (int s = 0; s < kTileMaxSlots; ++s) {
+                        const int pair = lane + 32 * s;
+                        if (pair < half) {
+                            reinterpret_cast<double2*>(scr_s)[pair] = accS[s];
+                            if (DRIFT) {
+                                const double j0 = static_cast<double>(2 * pair), Pd = static_cast<double>(P);
+                                reinterpret_cast<double2*>(scr_u)[pair] = make_double2(
+                                    fma(Pd, accT[s].x, j0 * accS[s].x), fma(Pd, accT[s].y, (j0 + 1.0) * accS[s].y));
+                            }
+                        }
+                        accS[s] = accT[s] = make_double2(0.0, 0.0);
+                    }
+                    __syncwarp();
+                    for (int j = lane; j <= half; j += 32) {
+                        const bool self = (j == 0) || (j == half);
+                        const double sa = scr_s[j], sb = self ? 0.0 : scr_s[P - j];
+                        double* xr = X + j * xrow + slot;
+                        xr[0] = sa + sb;
+                        xr[NBW] = self ? 0.0 : sa - sb;
+                        if (DRIFT) {
+                            const double ua = scr_u[j], ub = self ? 0.0 : scr_u[P - j];
+                            xr[2 * NBW] = ua + ub;
+                            xr[3 * NBW] = self ? 0.0 : ua - ub;
+                        }
+                    }
+                    __syncwarp();
+                    pin = 0;
+                    ++slot;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+
+        // outputs of the group: lane = output row (0 = mean, 1..N = Q_k, N+1..2N = I_k)
+        for (int vb = 0; vb < NV; vb += 32) {
+            const int v = vb + lane;
+            const bool active = v < NV;
+            const int vv = active ? v : 0;
+            const double* trow = t1 + vv * L.ldt;
+            const double* urow = t2 + vv * L.ldt;
+            const double* x1 = X + (vv <= N ? 0 : NBW);          // cosine rows read A, sine rows read B
+            const double* x2 = X + (vv <= N ? 3 * NBW : 2 * NBW);  // drift: cosine rows read BU, sine rows read AU
+            double acc[NBW];
+#pragma unroll
+            for (int s = 0; s < NBW; ++s) acc[s] = 0.0;
+#pragma unroll 4
+            for (int j = 0; j <= half; ++j) {
+                const double tv = trow[j];
+                if (NBW == 1) {
+                    acc[0] = fma(tv, x1[j * xrow], acc[0]);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < NBW; s += 2) {
+                        const double2 xv = *reinterpret_cast<const double2*>(x1 + j * xrow + s);
+                        acc[s] = fma(tv, xv.x, acc[s]);
+                        acc[s + 1] = fma(tv, xv.y, acc[s + 1]);
+                    }
+                }
+                if (DRIFT) {
+                    const double uv = urow[j];
+                    if (NBW == 1) {
+                        acc[0] = fma(uv, x2[j * xrow], acc[0]);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NBW; s += 2) {
+                            const double2 xv = *reinterpret_cast<const double2*>(x2 + j * xrow + s);
+                            acc[s] = fma(uv, xv.x, acc[s]);
+                            acc[s + 1] = fma(uv, xv.y, acc[s + 1]);
+                        }
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int s = 0; s < NBW; ++s) {
+                    if (s < nb) {
+                        const long long b = b0 + s;
+                        const double val = acc[s] / Rd;
+                        if (v == 0) {
+                            p.dc[b] = val;
+                        } else {
+                            p.qi[b * static_cast<long long>(2 * N) + (v - 1)] = val;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 constexpr int kDirectThreads = 256;
 constexpr int kDirectKB = 8;
 constexpr int kDirectResync = 64;

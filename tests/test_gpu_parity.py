@@ -102,6 +102,26 @@ def test_demod_vs_oracle_general(torch_mod, ctx, f_samp, f_mod, n, nh):
         assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
 
 
+@pytest.mark.parametrize("name", ["cfg1_quickstart", "fallback_m16"])
+def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
+    """Short periods take the barrier-free tile kernel; DFK_NO_TILE routes the same data through the CTA-per-buffer
+    fold kernel.  Both must sit at the reference's rounding floor."""
+    g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, name)
+    x = np.tile(x[: (len(x) // R) * R], 40)  # enough buffers for every warp of several CTAs, ragged last group
+    x = x[: (len(x) // R - 3) * R]
+    qi_tile, dc_tile = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    monkeypatch.setenv("DFK_NO_TILE", "1")
+    qi_fold, dc_fold = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    monkeypatch.delenv("DFK_NO_TILE")
+    nb = len(g["qi"])
+    ref = np.tile(g["qi"], (40, 1))[: len(qi_tile)]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(qi_tile - ref) / scale) <= IQ_TOL
+    assert np.max(np.abs(qi_fold - ref) / scale) <= IQ_TOL
+    assert np.max(np.abs(qi_tile - qi_fold) / scale) <= 3e-13
+    assert np.max(np.abs(dc_tile - dc_fold)) <= 1e-14
+
+
 def test_demod_unaligned_pointer_takes_direct_path(torch_mod, ctx, golden):
     g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, "cfg1_quickstart")
     nbuf = len(x) // R
