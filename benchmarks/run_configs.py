@@ -86,12 +86,13 @@ def nls_case(ctx, name, f_samp, n, ndata, channels, seconds, reps, m=6.0, init_m
     del x, qi, dc, rows
 
 
-def ekf_case(ctx, name, channels, seconds, reps, time_major, note=""):
+def ekf_case(ctx, name, channels, seconds, reps, time_major, note="", start_s=0.0):
     f_samp, f_mod, n = 200e3, 1000.0, 20
     R = int(f_samp / f_mod * n)
     T = int(seconds * f_samp)
+    k0 = int(start_s * f_samp) // R * R
     x = torch.empty(channels * T, dtype=torch.float64, device="cuda")
-    ctx.synth_snr_dev(x.data_ptr(), T, channels, f_samp, f_mod, 6.0, dphi=2 * np.pi / channels, seed=3)
+    ctx.synth_snr_slab_dev(x.data_ptr(), T, channels, T, k0, f_samp, f_mod, 6.0, dphi=2 * np.pi / channels, seed=3)
     z = x.view(channels, T)
     ld_t, ld_c = 1, T
     if time_major:
@@ -99,9 +100,20 @@ def ekf_case(ctx, name, channels, seconds, reps, time_major, note=""):
         ld_t, ld_c = channels, 1
     rows = torch.empty((channels, T // R, 8), dtype=torch.float64, device="cuda")
     opts = _lib.default_ekf_opts()
-    t = timed(lambda: ctx.ekf_dev(z.data_ptr(), T, channels, ld_t, ld_c, R, f_samp, f_mod, opts, rows.data_ptr()), reps)
+    state = torch.zeros((channels, 32), dtype=torch.float64, device="cuda")
+    if k0 > 0:  # a slab late in the record: start from a converged-looking state
+        state[:, 0], state[:, 1], state[:, 4], state[:, 30] = 1.0, 6.0, 1.15, 1e-4
+        state[:, 2] = torch.arange(channels, device="cuda") * (2 * np.pi / channels)
+        for i in range(5):
+            state[:, 5 + 6 * i] = 1e-6
+    keep = state.clone()
+
+    def run():
+        state.copy_(keep)
+        ctx.ekf_stream_dev(z.data_ptr(), T, channels, ld_t, ld_c, R, f_samp, f_mod, opts, k0, state.data_ptr(), rows.data_ptr())
+    t = timed(run, reps)
     r = rows.cpu().numpy()
-    out = {"config": name, "note": note, "channels": channels, "samples_per_channel": T, "layout": "time-major" if time_major else "channel-major",
+    out = {"config": name, "note": note, "start_s": start_s, "channels": channels, "samples_per_channel": T, "layout": "time-major" if time_major else "channel-major",
            "ekf_ms": t, "samples_per_s": channels * T / t * 1e3, "steps_per_s_per_channel": T / t * 1e3,
            "read_GBps": channels * T * 8 / t / 1e6, "m_last_mean": float(r[:, -1, 1].mean()), "m_last_std": float(r[:, -1, 1].std())}
     print(json.dumps(out), flush=True)
@@ -137,6 +149,9 @@ def main():
         elif c == "cfg4":
             ekf_case(ctx, "cfg4", 4096, 1.0, max(1, args.reps // 2), False, note="4096 channels x 1 s of the 100 s config")
             ekf_case(ctx, "cfg4", 4096, 1.0, max(1, args.reps // 2), True, note="4096 channels x 1 s of the 100 s config")
+        elif c == "cfg4late":
+            ekf_case(ctx, "cfg4late", 4096, 0.25, 1, False, note="slab starting at t = 90 s", start_s=90.0)
+            ekf_case(ctx, "cfg4late", 4096, 0.25, 1, False, note="slab starting at t = 0 s", start_s=0.0)
         elif c == "cfg4small":
             ekf_case(ctx, "cfg4small", 4096, 0.1, 1, False)
             ekf_case(ctx, "cfg4small", 4096, 0.1, 1, True)

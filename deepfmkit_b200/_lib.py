@@ -61,6 +61,10 @@ SYMBOLS = {
     "dfk_nls_fit_batch_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
                                              ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
+    "dfk_ekf_stream_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _i64,
+                                          _vp, _vp]),
+    "dfk_synth_snr_slab_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d,
+                                              ctypes.c_uint64]),
     "dfk_synth_snr_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d, ctypes.c_uint64]),
     "dfk_nls_fit_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
@@ -185,6 +189,16 @@ class Context:
     def ekf_dev(self, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, rows_ptr):
         _check(self.lib, self.lib.dfk_ekf_dev(self._h, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod,
                                               ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def ekf_stream_dev(self, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, k0, state_ptr, rows_ptr):
+        _check(self.lib, self.lib.dfk_ekf_stream_dev(self._h, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod,
+                                                     ctypes.byref(opts) if opts is not None else None, k0, state_ptr,
+                                                     rows_ptr))
+
+    def synth_snr_slab_dev(self, x_ptr, T, C, ld_c, t0, f_samp, f_mod, m, amp=1.0, visibility=1.0, phi0=0.0, dphi=0.0,
+                           psi0=0.0, snr_db=40.0, seed=0):
+        _check(self.lib, self.lib.dfk_synth_snr_slab_dev(self._h, x_ptr, T, C, ld_c, t0, f_samp, f_mod, m, amp,
+                                                         visibility, phi0, dphi, psi0, snr_db, int(seed)))
 
     def synth_snr_dev(self, x_ptr, T, C, f_samp, f_mod, m, amp=1.0, visibility=1.0, phi0=0.0, dphi=0.0, psi0=0.0,
                       snr_db=40.0, seed=0):

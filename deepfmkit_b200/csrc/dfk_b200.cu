@@ -712,7 +712,15 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
 
 int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c, int64_t R,
                 double f_samp, double f_mod, const dfk_ekf_opts* opts, double* rows_dev) {
+    return dfk_ekf_stream_dev(ctx, z_dev, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, 0, nullptr, rows_dev);
+}
+
+int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c, int64_t R,
+                       double f_samp, double f_mod, const dfk_ekf_opts* opts, int64_t k0, double* state_dev,
+                       double* rows_dev) {
     DFK_ENTER(ctx);
+    if (k0 < 0 || (R > 0 && k0 % R != 0)) return fail(DFK_ERR_ARG, "k0 must be a non-negative multiple of R");
+    if (k0 > 0 && !state_dev) return fail(DFK_ERR_ARG, "a continuation slab needs the carried state");
     if (T < 0 || C < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry: T=%lld C=%lld R=%lld", (long long)T, (long long)C, (long long)R);
     if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
     if (T == 0 || C == 0) return DFK_OK;
@@ -726,11 +734,15 @@ int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t
     if (rc) return rc;
     cudaStream_t st = ctx->stream();
     double* stats = static_cast<double*>(ctx->stats.ptr);
-    const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
-    dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats);
-    ctx->launches++;
-    DFK_CUDA(cudaGetLastError());
+    if (k0 == 0) {  // initial dc and default measurement variance come from the first (or only) slab
+        const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
+        dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats);
+        ctx->launches++;
+        DFK_CUDA(cudaGetLastError());
+    }
     dfk::EkfLaunch a;
+    a.k0 = k0;
+    a.state = state_dev;
     for (int i = 0; i < 4; ++i) a.init[i] = opts->init[i];
     for (int i = 0; i < 5; ++i) {
         a.p0[i] = opts->p0_diag[i];
@@ -772,8 +784,17 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
 int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double f_samp, double f_mod, double m,
                       double amp, double visibility, double phi0, double dphi, double psi0, double snr_db,
                       uint64_t seed) {
+    return dfk_synth_snr_slab_dev(ctx, x_dev, T, C, T, 0, f_samp, f_mod, m, amp, visibility, phi0, dphi, psi0, snr_db,
+                                  seed);
+}
+
+int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, int64_t ld_c, int64_t t0, double f_samp,
+                           double f_mod, double m, double amp, double visibility, double phi0, double dphi,
+                           double psi0, double snr_db, uint64_t seed) {
     DFK_ENTER(ctx);
     if (T < 0 || C < 0) return fail(DFK_ERR_ARG, "bad geometry");
+    if (t0 < 0 || (t0 & 1)) return fail(DFK_ERR_ARG, "t0 must be even and non-negative");
+    if (ld_c < T) return fail(DFK_ERR_ARG, "channel stride shorter than the slab");
     if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
     if (T == 0 || C == 0) return DFK_OK;
     if (!x_dev) return fail(DFK_ERR_ARG, "null device pointer");
@@ -781,6 +802,8 @@ int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double 
     p.x = x_dev;
     p.T = T;
     p.C = C;
+    p.t0 = t0;
+    p.ld_c = ld_c;
     const double per = f_samp / f_mod;
     p.P = (per == std::floor(per) && per >= 1.0 && per < 9e15) ? static_cast<long long>(per) : 0;
     p.f_ratio = f_mod / f_samp;

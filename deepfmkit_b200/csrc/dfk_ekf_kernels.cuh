@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(kStatsThreads) channel_stats_kernel(const doub
     }
 }
 
+constexpr int kEkfStateStride = 32;  // doubles per channel in a carried state: x[5], P[25], r, spare
+
 struct EkfLaunch {
+    long long k0;   // absolute index of the first sample of this call (a multiple of R)
+    double* state;  // carried filter state, C x kEkfStateStride (nullptr: single-call mode)
     double init[4];
     double p0[5];
     double q[5];
@@ -63,20 +67,32 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const double* __restri
     const long long c = blockIdx.x * static_cast<long long>(kEkfThreads) + threadIdx.x;
     if (c >= C) return;
     EkfState s;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s.x[i] = a.init[i];
-    s.x[4] = stats[2 * c];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) s.P[i][j] = (i == j) ? a.p0[i] : 0.0;
-    }
     EkfConsts k;
     k.w_m = a.w_m;
     k.f_samp = a.f_samp;
 #pragma unroll
     for (int i = 0; i < 5; ++i) k.q[i] = a.q[i];
-    k.r = (a.r_val == a.r_val) ? a.r_val : stats[2 * c + 1];
+    double* carried = a.state ? a.state + c * kEkfStateStride : nullptr;
+    if (carried && a.k0 > 0) {  // continuation slab: resume the filter where the previous call left it
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s.x[i] = carried[i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s.P[i][j] = carried[5 + 5 * i + j];
+        }
+        k.r = carried[30];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.x[i] = a.init[i];
+        s.x[4] = stats[2 * c];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s.P[i][j] = (i == j) ? a.p0[i] : 0.0;
+        }
+        k.r = (a.r_val == a.r_val) ? a.r_val : stats[2 * c + 1];
+    }
 
     const double* zc = z + c * ld_c;
     const long long nbuf = T / R;
@@ -100,7 +116,7 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const double* __restri
 #pragma unroll 1
         for (int i = 0; i < lim; ++i) {
             const long long t = t0 + i;
-            ekf_step(s, stage[i][threadIdx.x], t, k);
+            ekf_step(s, stage[i][threadIdx.x], a.k0 + t, k);
             if (t + 1 == next_snap) {
                 const long long idx = next_snap / R - 1;
                 if (idx < nbuf) {
@@ -111,6 +127,16 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const double* __restri
                 next_snap += R;
             }
         }
+    }
+    if (carried) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) carried[i] = s.x[i];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) carried[5 + 5 * i + j] = s.P[i][j];
+        }
+        carried[30] = k.r;
     }
 }
 

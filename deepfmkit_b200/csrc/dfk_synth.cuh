@@ -24,6 +24,8 @@ DFK_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 struct SynthParams {
     double* x;
     long long T, C;
+    long long t0;    // absolute index of the first sample generated (even); the stream is a function of absolute t
+    long long ld_c;  // output samples between consecutive channels
     long long P;  // samples per modulation period when it is a whole number, else 0
     double f_ratio;  // f_mod / f_samp
     double m, amp, vis, phi0, dphi, psi0;
@@ -45,7 +47,8 @@ __global__ void __launch_bounds__(256) synth_snr_kernel(const SynthParams p) {
     const long long total = pairs_per_ch * p.C;
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256ll) {
         const long long c = i / pairs_per_ch;
-        const long long t0 = (i - c * pairs_per_ch) * 2;
+        const long long tl = (i - c * pairs_per_ch) * 2;  // index inside the slab
+        const long long t0 = p.t0 + tl;                  // absolute sample index
         const double phi = p.phi0 + static_cast<double>(c) * p.dphi;
         const double sigma = clean_ac_rms(p.amp, p.vis, phi, p.m) * p.sigma_scale;
         uint32_t r[4];
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(256) synth_snr_kernel(const SynthParams p) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const long long t = t0 + e;
-            if (t >= p.T) break;
+            if (tl + e >= p.T) break;
             double frac;
             if (p.P > 0) {
                 frac = static_cast<double>(t % p.P) / static_cast<double>(p.P);
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(256) synth_snr_kernel(const SynthParams p) {
             }
             const double th = cospi(2.0 * frac + p.psi0 * (1.0 / kPi));
             const double clean = p.amp * (1.0 + p.vis * cos(phi + p.m * th));
-            p.x[c * p.T + t] = fma(sigma, g[e], clean);
+            p.x[c * p.ld_c + tl + e] = fma(sigma, g[e], clean);
         }
     }
 }

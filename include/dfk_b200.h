@@ -130,6 +130,16 @@ int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t 
 int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c,
                 int64_t R, double f_samp, double f_mod, const dfk_ekf_opts* opts, double* rows_dev);
 
+/* The same filter fed slab by slab, for records that do not fit the GPU (cfg 4: 655 GB): samples
+ * k0 .. k0+T-1 of every channel per call, k0 and T multiples of R.  state_dev (C x 32 doubles: x[5],
+ * P[25], r) carries the filter between calls; the call with k0 == 0 initialises it (initial dc and the
+ * default measurement variance then come from this first slab instead of the whole record, the one
+ * place the slab-wise result departs from EKFFitter.fit on the full record).
+ * rows_dev: C x (T/R) x DFK_ROW_STRIDE for this slab. */
+int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c,
+                       int64_t R, double f_samp, double f_mod, const dfk_ekf_opts* opts, int64_t k0,
+                       double* state_dev, double* rows_dev);
+
 /* 'snr'-mode synthetic record (physics.py:475-530) generated on the device with a counter-based
  * RNG: y = A(1 + C cos(phi0 + m cos(2 pi f_mod t + psi0))) + sigma N(0,1), sigma from snr_db.
  * Statistically (not bitwise) equivalent to the reference's MT19937 stream.  C channels,
@@ -137,6 +147,12 @@ int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t
 int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double f_samp, double f_mod,
                       double m, double amp, double visibility, double phi0, double dphi, double psi0,
                       double snr_db, uint64_t seed);
+
+/* Samples t0 .. t0+T-1 of the same streams (t0 even), channel c written at x_dev + c * ld_c: any slab of
+ * a long record can be produced on its own, on any GPU. */
+int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, int64_t ld_c, int64_t t0, double f_samp,
+                           double f_mod, double m, double amp, double visibility, double phi0, double dphi,
+                           double psi0, double snr_db, uint64_t seed);
 
 /* ---- host-pointer entry points (what the reference-side shim binds) ---------------------- */
 /* StandardNLSFitter.fit on one host record (fitters.py:330-428): nsamp samples, buffers of R,

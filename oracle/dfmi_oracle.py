@@ -351,7 +351,8 @@ EKF_Q_DIAG = (1e-8, 1e-8, 1e-6, 1e-6, 1e-8)
 
 def ekf_track(x: np.ndarray, f_samp: float, f_mod: float, n: int,
               init_a: float = 1.6, init_m: float = 6.0, init_phi: float = 0.0, init_psi: float = 0.0,
-              p0_diag=EKF_P0_DIAG, q_diag=EKF_Q_DIAG, r_val: float | None = None) -> np.ndarray:
+              p0_diag=EKF_P0_DIAG, q_diag=EKF_Q_DIAG, r_val: float | None = None,
+              init_dc: float | None = None) -> np.ndarray:
     """5-state random-walk EKF with scalar measurement, state snapshot every R samples.
 
     State [a, m, phi, psi, dc]; time is absolute, t_k = k / f_samp (fitters.py:263).
@@ -359,7 +360,9 @@ def ekf_track(x: np.ndarray, f_samp: float, f_mod: float, n: int,
     """
     z = np.asarray(x, dtype=float).ravel()
     R, _, nbuf = buffer_geometry(len(z), f_samp, f_mod, n)
-    state = np.array([init_a, init_m, init_phi, init_psi, np.mean(z)])
+    # init_dc is not a reference option: it lets tests of the slab-wise GPU entry point start the filter from the
+    # first slab's mean, as that entry point does (the reference always uses the whole record's mean).
+    state = np.array([init_a, init_m, init_phi, init_psi, np.mean(z) if init_dc is None else init_dc])
     cov = np.diag(p0_diag).astype(float)
     q_mat = np.diag(q_diag).astype(float)
     if r_val is None:

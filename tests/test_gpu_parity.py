@@ -255,6 +255,45 @@ def test_ekf_batch_layouts_agree(torch_mod, golden):
     assert np.max(np.abs(a[0, :, :5] - ref[:, :5])) < 1e-9
 
 
+def test_ekf_slabwise_equals_whole_record(torch_mod, ctx, golden):
+    """dfk_ekf_stream_dev over three slabs with carried state == one pass over the record (same initial dc and R)."""
+    from deepfmkit_b200 import _lib
+    torch = torch_mod
+    g = golden("ekf_default")
+    x = g["x"][:36000]
+    R, C = 4000, 3
+    z = np.stack([x, x[::-1].copy(), 0.5 * x + 0.1])
+    zd = torch.from_numpy(z).cuda()
+    state = torch.zeros((C, 32), dtype=torch.float64, device="cuda")
+    opts = _lib.default_ekf_opts()
+    parts = []
+    for k0, T in ((0, 12000), (12000, 8000), (20000, 16000)):
+        slab = zd[:, k0:k0 + T].contiguous()
+        rows = torch.empty((C, T // R, 8), dtype=torch.float64, device="cuda")
+        ctx.ekf_stream_dev(slab.data_ptr(), T, C, 1, T, R, 200e3, 1000.0, opts, k0, state.data_ptr(), rows.data_ptr())
+        ctx.synchronize()
+        parts.append(rows.cpu().numpy())
+    got = np.concatenate(parts, axis=1)
+    for c in range(C):
+        first = z[c, :12000]
+        ref = orc.ekf_track(z[c], 200e3, 1000.0, 20, r_val=np.var(first), init_dc=np.mean(first))
+        assert np.max(np.abs(got[c, :, :5] - ref[:, :5])) < 1e-9
+    with pytest.raises(RuntimeError):
+        ctx.ekf_stream_dev(zd.data_ptr(), 8000, C, 1, 36000, R, 200e3, 1000.0, opts, 4000, None, 0)
+
+
+def test_synth_slabs_tile_the_record(torch_mod, ctx):
+    torch = torch_mod
+    T, C = 30000, 3
+    whole = torch.empty((C, T), dtype=torch.float64, device="cuda")
+    ctx.synth_snr_dev(whole.data_ptr(), T, C, 200e3, 1000.0, 6.0, dphi=0.4, seed=21)
+    parts = torch.zeros((C, T), dtype=torch.float64, device="cuda")
+    for t0, n in ((0, 10000), (10000, 4000), (14000, 16000)):
+        ctx.synth_snr_slab_dev(parts.data_ptr() + t0 * 8, n, C, T, t0, 200e3, 1000.0, 6.0, dphi=0.4, seed=21)
+    ctx.synchronize()
+    assert torch.equal(whole, parts)
+
+
 # ---- the reference-facing Python API --------------------------------------------------------------
 def test_fitter_api_and_result_frame(torch_mod, golden):
     import pandas as pd
