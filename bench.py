@@ -63,6 +63,21 @@ def ncu_traffic_per_launch():
         return None
 
 
+def lm_roofline(counters, fits, nbuf, lm_ms, peak_tflops):
+    """FP64 rate of the LM launches from the work the kernels counted (SURVEY 8d's per-call costs, N harmonics):
+    model+Jacobian F_c = 3M + 90N + 2S, residual F_s = 3M + 12N + 2S with the Miller steps M counted on device,
+    S = 60 flop per sincos, F_m = 100 per damped solve."""
+    per = {k: v / fits for k, v in counters.items()}
+    flop_per_fit = (per["n_state"] * (90 * NDATA + 120) + per["n_ssq"] * (12 * NDATA + 120) + per["n_solve"] * 100 +
+                    3 * per["n_bessel_steps"])
+    achieved = flop_per_fit * nbuf / (lm_ms * 1e-3) / 1e12
+    return {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": achieved / peak_tflops if peak_tflops else None, "flop_per_fit": flop_per_fit,
+            "peak_source": "dfk_probe_fp64: DFMA chains measured on this GPU in this run",
+            "note": "algorithmic flops of the reference's formulation; the kernel's block-diagonal normal equations "
+                    "execute about half of the model+Jacobian figure"}
+
+
 # ---- clocks sampled during the timed region -------------------------------------------------------------
 class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -231,6 +246,7 @@ def run_gpu(args):
         ctx.profile_enable(False)
         counters = ctx.lm_counters(reset=True)
         head = rows[:4096].cpu().numpy()
+        fp64_peak = ctx.probe_fp64_tflops() if rank == 0 else None
 
     # sanity: the timed work produced real fits
     assert np.all(head[:, 6] == 0) and abs(head[:, 1].mean() - M_TRUE) < 1e-3, "bench fits are wrong"
@@ -291,7 +307,8 @@ def run_gpu(args):
                          "kernel_ms": demod_ms, "share_of_step": demod_ms / ms_per_step},
             "lm": {"kernel_ms_per_step": lm_ms, "share_of_step": lm_ms / ms_per_step,
                    "fits_per_sec": NBUF / (lm_ms * 1e-3),
-                   "per_fit": {k: v / fits for k, v in counters.items()}},
+                   "per_fit": {k: v / fits for k, v in counters.items()},
+                   "roofline": lm_roofline(counters, fits, NBUF, lm_ms, fp64_peak)},
             "cpu_baseline": {"value": n_cpu / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{n_cpu} buffers ({n_cpu * R / F_SAMP:.0f} s of the cfg2 record), "
                                        "oracle port of the reference's Pool schedule, pool start-up included"},

@@ -71,6 +71,7 @@ SYMBOLS = {
     "dfk_lm_counters_read": (ctypes.c_int, [_vp, ctypes.POINTER(LmCounters), _i32]),
     "dfk_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "dfk_profile_read": (ctypes.c_int, [_vp, c_double_p, ctypes.POINTER(_i64), _i32]),
+    "dfk_probe_fp64": (ctypes.c_int, [_vp, c_double_p]),
     "dfk_launch_count": (_i64, [_vp]),
     "dfk_demod_path": (ctypes.c_int, [_i64, _d]),
     "dfk_bessel_dev": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
@@ -245,6 +246,11 @@ class Context:
         n = (_i64 * 2)()
         _check(self.lib, self.lib.dfk_profile_read(self._h, ms, n, int(bool(reset))))
         return {"demod_ms": ms[0], "demod_regions": int(n[0]), "lm_ms": ms[1], "lm_regions": int(n[1])}
+
+    def probe_fp64_tflops(self) -> float:
+        v = ctypes.c_double()
+        _check(self.lib, self.lib.dfk_probe_fp64(self._h, ctypes.byref(v)))
+        return float(v.value)
 
     def launch_count(self) -> int:
         return int(self.lib.dfk_launch_count(self._h))

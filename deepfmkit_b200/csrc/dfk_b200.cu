@@ -228,6 +228,14 @@ bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeom
     return found;
 }
 
+template <bool DRIFT, int SLOTS>
+int launch_fold_t(const dfk::FoldParams& p, size_t smem, int grid, cudaStream_t st) {
+    DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_kernel<DRIFT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    dfk::demod_fold_kernel<DRIFT, SLOTS><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+    return DFK_OK;
+}
+
 template <bool DRIFT, int NBW>
 int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid, cudaStream_t st) {
     DFK_CUDA(cudaFuncSetAttribute(dfk::demod_tile_kernel<DRIFT, NBW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -323,15 +331,24 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
         p.nstages = g.nstages;
         for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];
         const int grid = static_cast<int>(std::min<int64_t>(nbuf, static_cast<int64_t>(ctx->sm_count) * g.ctas_per_sm));
+        const int slots = (p.P / 2 + dfk::kFoldConsumers - 1) / dfk::kFoldConsumers;
+        int rc;
         if (pl.drift) {
-            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(g.smem)));
-            dfk::demod_fold_kernel<true><<<grid, dfk::kFoldThreads, g.smem, st>>>(p);
+            switch (slots) {
+                case 1: rc = launch_fold_t<true, 1>(p, g.smem, grid, st); break;
+                case 2: rc = launch_fold_t<true, 2>(p, g.smem, grid, st); break;
+                case 3: rc = launch_fold_t<true, 3>(p, g.smem, grid, st); break;
+                default: rc = launch_fold_t<true, 4>(p, g.smem, grid, st); break;
+            }
         } else {
-            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(g.smem)));
-            dfk::demod_fold_kernel<false><<<grid, dfk::kFoldThreads, g.smem, st>>>(p);
+            switch (slots) {
+                case 1: rc = launch_fold_t<false, 1>(p, g.smem, grid, st); break;
+                case 2: rc = launch_fold_t<false, 2>(p, g.smem, grid, st); break;
+                case 3: rc = launch_fold_t<false, 3>(p, g.smem, grid, st); break;
+                default: rc = launch_fold_t<false, 4>(p, g.smem, grid, st); break;
+            }
         }
+        if (rc) return rc;
     } else {
         const int grid = static_cast<int>(std::min<int64_t>(nbuf, static_cast<int64_t>(ctx->sm_count) * 8));
         dfk::demod_direct_kernel<<<grid, dfk::kDirectThreads, 0, st>>>(x, nbuf, bpc, ld_c, R, N, w0, qi, dc);
@@ -858,6 +875,34 @@ int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int3
             ctx->prof_n[k] = 0;
         }
     }
+    return DFK_OK;
+}
+
+int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out) {
+    DFK_ENTER(ctx);
+    if (!tflops_out) return fail(DFK_ERR_ARG, "null output pointer");
+    int rc = ensure(ctx, ctx->misc, 256);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream();
+    cudaEvent_t e0, e1;
+    DFK_CUDA(cudaEventCreate(&e0));
+    DFK_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = ctx->sm_count * 8;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition warms up
+        DFK_CUDA(cudaEventRecord(e0, st));
+        dfk::fp64_probe_kernel<<<blocks, 256, 0, st>>>(iters, 0.5, static_cast<double*>(ctx->misc.ptr));
+        DFK_CUDA(cudaEventRecord(e1, st));
+        DFK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        DFK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    DFK_CUDA(cudaGetLastError());
+    const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
+    *tflops_out = flops / (best_ms * 1e-3) / 1e12;
     return DFK_OK;
 }
 

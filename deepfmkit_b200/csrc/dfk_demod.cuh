@@ -76,7 +76,8 @@ DFK_D void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
-template <bool DRIFT>
+// SLOTS = ceil(P / 2 / 256): column pairs per consumer thread (all but the last slot are full for every thread)
+template <bool DRIFT, int SLOTS>
 __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FoldSmem L = fold_smem_layout(p.P, p.pps, p.nstages, p.N, DRIFT);
@@ -147,24 +148,24 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
     int stage = 0;
     uint32_t phase = 0;
     for (long long b = blockIdx.x; b < p.nbuf; b += gridDim.x) {
-        double2 accS[kFoldMaxSlots], accT[kFoldMaxSlots];
+        double2 accS[SLOTS], accT[SLOTS];
 #pragma unroll
-        for (int s = 0; s < kFoldMaxSlots; ++s) {
+        for (int s = 0; s < SLOTS; ++s) {
             accS[s] = make_double2(0.0, 0.0);
             accT[s] = make_double2(0.0, 0.0);
         }
+        const bool last_ok = tid + (SLOTS - 1) * kFoldConsumers < half;
         for (int q = 0; q < chunks; ++q) {
             const int np = min(p.pps, p.periods - q * p.pps);
             mbar_wait(&full[stage], phase);
-            const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+            const double2* row = reinterpret_cast<const double2*>(stage_base + static_cast<size_t>(stage) * L.stage_doubles) + tid;
+            double cg = static_cast<double>(q * p.pps);
+#pragma unroll 4
             for (int c = 0; c < np; ++c) {
-                const double2* row = reinterpret_cast<const double2*>(sm + c * P);
-                const double cg = static_cast<double>(q * p.pps + c);
 #pragma unroll
-                for (int s = 0; s < kFoldMaxSlots; ++s) {
-                    const int pair = tid + s * kFoldConsumers;
-                    if (pair < half) {
-                        const double2 v = row[pair];
+                for (int s = 0; s < SLOTS; ++s) {
+                    if (s < SLOTS - 1 || last_ok) {
+                        const double2 v = row[s * kFoldConsumers];
                         accS[s].x += v.x;
                         accS[s].y += v.y;
                         if (DRIFT) {
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
                         }
                     }
                 }
+                row += half;
+                if (DRIFT) cg += 1.0;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
 
         consumer_bar();  // everyone is done with the previous buffer's folded arrays
 #pragma unroll
-        for (int s = 0; s < kFoldMaxSlots; ++s) {
+        for (int s = 0; s < SLOTS; ++s) {
             const int pair = tid + s * kFoldConsumers;
             if (pair < half) {
                 reinterpret_cast<double2*>(sm_s)[pair] = accS[s];

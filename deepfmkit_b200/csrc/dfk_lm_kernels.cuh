@@ -139,4 +139,21 @@ __global__ void bessel_kernel(const double* __restrict__ x, long long n, int nma
     if (i < n) bessel_j_upto(x[i], nmax, out + i * (nmax + 1), 1);
 }
 
+// FP64 FMA throughput probe: 8 independent DFMA chains per thread (the denominator bench.py quotes the LM
+// kernel's fp64 rate against; MEASURED_PEAKS.json has no fp64 figure).
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double seed, double* __restrict__ sink) {
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + 1e-3 * (threadIdx.x + i);
+    const double m = 1.0 - 1e-9, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += a[i];
+    if (t == 123.456) sink[0] = t;  // keeps the chains alive without writing in practice
+}
+
 }  // namespace dfk

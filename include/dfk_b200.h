@@ -174,6 +174,9 @@ int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset);
  * and the number of timed regions of each class. */
 int dfk_profile_enable(dfk_ctx* ctx, int32_t on);
 int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int32_t reset);
+/* Measured fp64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per thread, best of 3):
+ * the denominator for the LM kernel's fraction of the FP64 roofline. */
+int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out);
 /* Kernel launches issued through this context since creation (bench.py's gpu_launches). */
 int64_t dfk_launch_count(dfk_ctx* ctx);
 /* Which demod kernel the given geometry selects: 1 = folded TMA kernel, 0 = general kernel. */
