@@ -122,6 +122,63 @@ def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
     assert np.max(np.abs(dc_tile - dc_fold)) <= 1e-14
 
 
+@pytest.mark.parametrize("P,n,nh", [(2048, 3, 10), (1536, 2, 7), (1000, 1, 64), (6, 50, 2), (2, 40, 1), (256, 5, 31),
+                                    (258, 4, 16), (200, 3, 40), (2050, 2, 5), (75, 20, 10)])
+def test_demod_period_and_harmonic_extremes(torch_mod, ctx, P, n, nh):
+    """Largest folded period (2048), smallest (2), the tile/fold boundary (256/258), N = 1 and N = 64, a table too big
+    for the tile kernel (N = 40 at P = 200), and periods the fold cannot take (2050 > max, 75 odd)."""
+    from deepfmkit_b200 import _lib
+    f_mod = 1000.0
+    f_samp = f_mod * P
+    R = P * n
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    assert _lib.demod_path(R, w0) == (1 if (P % 2 == 0 and P <= 2048) else 0)
+    rng = np.random.RandomState(P + n)
+    nbuf = 37
+    t = np.arange(nbuf * R)
+    x = 1.0 + np.cos(0.7 + 3.0 * np.cos(2 * np.pi * t / P + 0.2)) + 0.01 * rng.randn(nbuf * R)
+    qi, dc = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    for b in (0, 1, 17, nbuf - 1):
+        buf = x[b * R:(b + 1) * R]
+        ref = orc.lockin_means(buf, w0, nh)
+        assert np.max(np.abs(qi[b] - ref)) <= IQ_TOL * max(np.abs(ref).max(), 1e-3), (P, n, nh, b)
+        assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
+
+
+def test_empty_and_degenerate_calls(torch_mod, ctx):
+    from deepfmkit_b200 import _lib, nls_fit_batch
+    torch = torch_mod
+    w0 = orc.rad_per_sample(200e3, 1000.0)
+    ctx.demod(0, 0, 4000, 10, w0, 0, 0)  # nothing to do, null pointers allowed
+    ctx.nls_fit_dev(0, 0, 4000, 10, w0, [1.6, 6.0, 0, 0], True, None, 0)
+    assert ctx.nls_fit_host(np.zeros(100), 4000, 10, w0, [1.6, 6.0, 0, 0]).shape == (0, 8)
+    assert nls_fit_batch(np.zeros((3, 100)), 200e3, 1000.0, 20).shape == (3, 0, 8)
+    x = torch.zeros(8000, dtype=torch.float64, device="cuda")
+    rows = torch.zeros((2, 8), dtype=torch.float64, device="cuda")
+    for bad in (dict(N=0), dict(N=65), dict(w0=0.0), dict(w0=float("nan")), dict(R=0)):
+        kw = dict(N=10, w0=w0, R=4000)
+        kw.update(bad)
+        with pytest.raises(RuntimeError):
+            ctx.nls_fit_dev(x.data_ptr(), 2, kw["R"], kw["N"], kw["w0"], [1.6, 6.0, 0, 0], True, None, rows.data_ptr())
+    # an all-zero and a non-finite record are data, not errors; the flags follow the reference: the zero record
+    # "fits" with the amplitude driven to nothing (fitok 0), the NaN buffer stays unfitted (fitok 2, ssq NaN)
+    ctx.nls_fit_dev(x.data_ptr(), 2, 4000, 10, w0, [1.6, 6.0, 0, 0], True, None, rows.data_ptr())
+    ctx.synchronize()
+    r = rows.cpu().numpy()
+    ref0 = orc.nls_fit(np.zeros(8000), 200e3, 1000.0, 20, 10)
+    assert np.array_equal(r[:, 6], ref0[:, 6]) and np.all(r[:, 0] < 1e-100) and np.all(r[:, 5] == 0)
+    x[100] = float("nan")
+    ctx.nls_fit_dev(x.data_ptr(), 2, 4000, 10, w0, [1.6, 6.0, 0, 0], True, None, rows.data_ptr())
+    ctx.synchronize()
+    r = rows.cpu().numpy()
+    xn = np.zeros(8000)
+    xn[100] = np.nan
+    with np.errstate(all="ignore"):
+        refn = orc.nls_fit(xn, 200e3, 1000.0, 20, 10)
+    assert np.array_equal(r[:, 6], refn[:, 6]) and r[0, 6] == 2 and np.isnan(r[0, 5])
+    assert np.array_equal(r[0, :4], refn[0, :4])
+
+
 def test_demod_unaligned_pointer_takes_direct_path(torch_mod, ctx, golden):
     g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, "cfg1_quickstart")
     nbuf = len(x) // R
