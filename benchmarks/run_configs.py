@@ -73,6 +73,11 @@ def nls_case(ctx, name, f_samp, n, ndata, channels, seconds, reps, m=6.0, init_m
                               seeded, opts, rows.data_ptr())
     t_all = timed(whole, reps)
     cnt = ctx.lm_counters(reset=True)
+    ctx.profile_enable(True)
+    ctx.profile_read(reset=True)
+    whole()
+    prof = ctx.profile_read(reset=True)
+    ctx.profile_enable(False)
     r = rows.cpu().numpy()
     alg = (8 * R + 8 * (2 * ndata + 1)) * nbuf
     fits = nbuf * (reps + 1)
@@ -81,7 +86,7 @@ def nls_case(ctx, name, f_samp, n, ndata, channels, seconds, reps, m=6.0, init_m
            "nls_ms": t_all, "lm_ms": t_all - t_demod, "buffers_per_s": nbuf / t_all * 1e3, "samples_per_s": nbuf * R / t_all * 1e3,
            "lm_fits_per_s": nbuf / max(t_all - t_demod, 1e-9) * 1e3,
            "fitok_counts": {str(int(k)): int(v) for k, v in zip(*np.unique(r[:, 6], return_counts=True))},
-           "m_mean": float(r[:, 1].mean()), "per_fit": {k: v / fits for k, v in cnt.items()}}
+           "prof": {k: round(v, 4) for k, v in prof.items()}, "m_mean": float(r[:, 1].mean()), "per_fit": {k: v / fits for k, v in cnt.items()}}
     print(json.dumps(out), flush=True)
     del x, qi, dc, rows
 

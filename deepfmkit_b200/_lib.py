@@ -242,10 +242,11 @@ class Context:
 
     def profile_read(self, reset=False) -> dict:
         """Summed device milliseconds and region counts: demod launches and LM launches."""
-        ms = (ctypes.c_double * 2)()
-        n = (_i64 * 2)()
+        ms = (ctypes.c_double * 3)()
+        n = (_i64 * 3)()
         _check(self.lib, self.lib.dfk_profile_read(self._h, ms, n, int(bool(reset))))
-        return {"demod_ms": ms[0], "demod_regions": int(n[0]), "lm_ms": ms[1], "lm_regions": int(n[1])}
+        return {"demod_ms": ms[0], "demod_regions": int(n[0]), "lm_ms": ms[1], "lm_regions": int(n[1]),
+                "seed_ms": ms[2], "seed_regions": int(n[2])}
 
     def probe_fp64_tflops(self) -> float:
         v = ctypes.c_double()

@@ -49,19 +49,20 @@ struct dfk_ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     int smem_per_sm = 0;
-    cudaStream_t own_stream = nullptr, copy_stream = nullptr, user_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr, user_stream = nullptr;
     bool use_user = false;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-    DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc, qi_seed, dc_seed;
     int64_t launches = 0;
     // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the
     // demod launch [0] and around the LM launches [1], summed on read
     bool profiling = false;
     static constexpr int kProfSlots = 512;
-    cudaEvent_t prof_ev[2][kProfSlots][2] = {};
-    int prof_used[2] = {0, 0};
-    double prof_ms[2] = {0.0, 0.0};
-    int64_t prof_n[2] = {0, 0};
+    cudaEvent_t prof_ev[3][kProfSlots][2] = {};
+    int prof_used[3] = {0, 0, 0};
+    double prof_ms[3] = {0.0, 0.0, 0.0};
+    int64_t prof_n[3] = {0, 0, 0};
     cudaStream_t stream() const { return use_user ? user_stream : own_stream; }
 };
 
@@ -88,7 +89,7 @@ int ensure(dfk_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 int prof_drain(dfk_ctx* ctx) {  // fold recorded event pairs into the totals (synchronises)
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         for (int i = 0; i < ctx->prof_used[k]; ++i) {
             DFK_CUDA(cudaEventSynchronize(ctx->prof_ev[k][i][1]));
             float ms = 0.f;
@@ -165,13 +166,21 @@ dfk::LmOpts to_opts(const dfk_lm_opts* o) {
 }
 
 // ---- demodulation -------------------------------------------------------------------------------
+// Shared memory left free on every SM next to a persistent demod CTA so that one block of the cold seed fits
+// (Bessel columns: (N+2) x 128 doubles) can co-reside and overlap with it; given up when it would cost the
+// ring too much (many harmonics).
+size_t seed_fit_reserve(int N) {
+    const size_t need = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double) + 2048;
+    return need <= 24 * 1024 ? need : 0;
+}
+
 struct FoldGeometry {
     int pps, nstages;
     size_t smem;
     int ctas_per_sm;
 };
 
-bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeometry* g) {
+bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, bool leave_room, FoldGeometry* g) {
     const int P = static_cast<int>(pl.P);
     // development overrides (tuning runs only): DFK_FOLD_STAGE_BYTES, DFK_FOLD_NSTAGES, DFK_FOLD_CTAS
     const int env_stage = env_int("DFK_FOLD_STAGE_BYTES", 0), env_nst = env_int("DFK_FOLD_NSTAGES", 0),
@@ -201,8 +210,9 @@ bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, FoldGeom
     int best_stage = 0;
     bool found = false;
     for (int ctas = 2; ctas >= 1; --ctas) {
-        const size_t budget = ctas == 2 ? static_cast<size_t>(ctx->smem_per_sm) / 2 - 1024
-                                        : static_cast<size_t>(ctx->max_smem_optin);
+        const size_t room = leave_room ? seed_fit_reserve(N) : 0;
+        const size_t budget = ctas == 2 ? (static_cast<size_t>(ctx->smem_per_sm) - room) / 2 - 1024
+                                        : static_cast<size_t>(ctx->max_smem_optin) - room;
         for (int target : stage_targets) {
             int q = target / (P * 8);
             if (q < 1) q = 1;
@@ -248,7 +258,7 @@ int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid,
 // Short periods (P <= 256) with contiguous buffers: the barrier-free tile kernel.  Returns 1 if it launched,
 // 0 if the geometry does not fit it, < 0 on error.
 int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int64_t R, int32_t N,
-                    double* qi, double* dc, cudaStream_t st) {
+                    double* qi, double* dc, bool leave_room, cudaStream_t st) {
     if (pl.P > dfk::kTileMaxPeriod || env_int("DFK_NO_TILE", 0)) return 0;
     const int P = static_cast<int>(pl.P), n = static_cast<int>(pl.periods);
     int nbw = 8;
@@ -262,7 +272,7 @@ int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int
     size_t smem = 0;
     for (; nst >= 2; --nst) {
         smem = dfk::tile_smem_layout(P, N, nbw, pps, nst, pl.drift).total;
-        if (smem <= static_cast<size_t>(ctx->max_smem_optin)) break;
+        if (smem <= static_cast<size_t>(ctx->max_smem_optin) - (leave_room ? seed_fit_reserve(N) : 0)) break;
     }
     if (nst < 2) return 0;
     dfk::TileParams p;
@@ -300,8 +310,9 @@ int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int
 }
 
 // nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
+// leave_room: keep enough shared memory free on each SM for a block of the seed fits that run beside this launch
 int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
-                 double* qi, double* dc, cudaStream_t st) {
+                 double* qi, double* dc, cudaStream_t st, bool leave_room = false) {
     if (nbuf == 0) return DFK_OK;
     dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
     const int env_drift = env_int("DFK_FOLD_DRIFT", -1);  // development override
@@ -310,12 +321,12 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
     int tiled = 0;
     if (pl.folded && aligned && ld_c == bpc * R) {
-        tiled = try_launch_tile(ctx, pl, x, nbuf, R, N, qi, dc, st);
+        tiled = try_launch_tile(ctx, pl, x, nbuf, R, N, qi, dc, leave_room, st);
         if (tiled < 0) return tiled;
     }
     if (tiled) {
         // launched above
-    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, &g)) {
+    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, leave_room, &g)) {
         dfk::FoldParams p;
         p.x = x;
         p.qi = qi;
@@ -371,16 +382,22 @@ int pick_lanes(const dfk_ctx* ctx, int64_t nfit, int N, int requested) {
     return g;
 }
 
-template <int G, int MINB>
+template <int G, int MINB, int TPB>
 int launch_first_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
-                 const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
-    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                   const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(N + 2) * TPB * sizeof(double);
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G, MINB, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    const int64_t fits_per_block = dfk::kLmThreads / G;
+    // keep the SM's L1/shared split at "all shared": a block of this kernel may share an SM with a demod CTA that
+    // needs > 200 kB, and an SM only changes its carve-out when it is idle
+    // (only the one-warp-block variant, which is the one that overlaps a demod launch: the bulk variant wants its L1)
+    if (TPB == 32)
+        DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G, MINB, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+    const int64_t fits_per_block = TPB / G;
     const int64_t blocks = (nfit + fits_per_block - 1) / fits_per_block;
     const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * 16));
-    dfk::lm_first_kernel<G, MINB><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
+    dfk::lm_first_kernel<G, MINB, TPB><<<grid, TPB, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
@@ -390,9 +407,9 @@ template <int G>
 int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
                  const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
     switch (env_int("DFK_LM_MINB", 4)) {  // development override: resident blocks per SM the kernel is compiled for
-        case 6: return launch_first_b<G, 6>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
-        case 8: return launch_first_b<G, 8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
-        default: return launch_first_b<G, 4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 6: return launch_first_b<G, 6, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 8: return launch_first_b<G, 8, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        default: return launch_first_b<G, 4, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
     }
 }
 
@@ -420,7 +437,12 @@ int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int
     int* list = count + 4;
     auto* counters = static_cast<dfk::LmCounts*>(ctx->counters.ptr);
     DFK_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
-    const int G = pick_lanes(ctx, nfit, N, opts ? opts->lanes_per_fit : 0);
+    const int requested = opts ? opts->lanes_per_fit : 0;
+    const int G = pick_lanes(ctx, nfit, N, requested);
+    if (requested == 0 && nfit <= 2 * static_cast<int64_t>(ctx->sm_count)) {
+        // a handful of fits: one warp per fit in one-warp blocks, spread over all SMs
+        rc = launch_first_b<32, 4, 32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+    } else
     switch (G) {
         case 1: rc = launch_first<1>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
         case 2: rc = launch_first<2>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
@@ -433,9 +455,11 @@ int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int
     const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
     DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     const int64_t warps = dfk::kLmThreads / 32;
     const int grid = static_cast<int>(std::min<int64_t>((nfit + warps - 1) / warps, static_cast<int64_t>(ctx->sm_count) * 8));
-    dfk::lm_retry_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, N, o, rows, list, count, counters);
+    dfk::lm_retry_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, N, o, map.row_mul, rows, list, count, counters);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
@@ -483,23 +507,50 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
     if (rc) return rc;
     rc = ensure(ctx, ctx->dc, static_cast<size_t>(nbuf) * sizeof(double));
     if (rc) return rc;
+    rc = ensure(ctx, ctx->retry, (static_cast<size_t>(nbuf) + 4) * sizeof(int));
+    if (rc) return rc;
+    rc = ensure_counters(ctx);
+    if (rc) return rc;
     double* qi = static_cast<double*>(ctx->qi.ptr);
     double* dc = static_cast<double*>(ctx->dc.ptr);
+    const dfk::GuessSrc cold = init_dev ? guess_rows(init_dev, init_stride, bpc, false) : guess_value(init);
+    const bool two_stage = seeded && !seed_row && bpc > 1;
+    if (two_stage) {
+        // fitters.py:404-405: buffer 0 of every channel is fitted cold before anything else.  Those C fits are a
+        // short, latency-bound chain, so they run on a side stream -- their own demodulation of the C first
+        // buffers, then the cold fits -- while the main stream demodulates the whole record.
+        rc = ensure(ctx, ctx->qi_seed, static_cast<size_t>(C) * 2 * N * sizeof(double));
+        if (rc) return rc;
+        rc = ensure(ctx, ctx->dc_seed, static_cast<size_t>(C) * sizeof(double));
+        if (rc) return rc;
+        double* qs = static_cast<double*>(ctx->qi_seed.ptr);
+        double* ds = static_cast<double*>(ctx->dc_seed.ptr);
+        cudaStream_t aux = ctx->aux_stream;
+        DFK_CUDA(cudaEventRecord(ctx->fork, st));
+        DFK_CUDA(cudaStreamWaitEvent(aux, ctx->fork, 0));
+        {
+            ProfScope ps(ctx, 2, aux);
+            rc = launch_demod(ctx, x, C, 1, ld_c, R, N, w0, qs, ds, aux);
+            if (rc) return rc;
+            const dfk::GuessSrc cold_c = init_dev ? guess_rows(init_dev, init_stride, 1, false) : guess_value(init);
+            rc = launch_lm(ctx, qs, C, {1, 0, bpc}, N, cold_c, ds, opts, rows, aux);
+            if (rc) return rc;
+        }
+        DFK_CUDA(cudaEventRecord(ctx->join, aux));
+    }
     {
         ProfScope ps(ctx, 0, st);
-        rc = launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st);
+        rc = launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st, two_stage);
     }
     if (rc) return rc;
     ProfScope ps(ctx, 1, st);
-    const dfk::GuessSrc cold = init_dev ? guess_rows(init_dev, init_stride, bpc, false) : guess_value(init);
-    if (!seeded || (bpc == 1 && !seed_row)) return launch_lm(ctx, qi, nbuf, {1, 0}, N, cold, dc, opts, rows, st);
+    if (!seeded || (bpc == 1 && !seed_row)) return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, cold, dc, opts, rows, st);
     if (seed_row) {  // continuation slab of a single record: everything starts from the stored row
-        return launch_lm(ctx, qi, nbuf, {1, 0}, N, guess_rows(seed_row, 0, nbuf, false), dc, opts, rows, st);
+        return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(seed_row, 0, nbuf, false), dc, opts, rows, st);
     }
-    rc = launch_lm(ctx, qi, C, {bpc, 0}, N, cold, dc, opts, rows, st);  // fitters.py:404-405, once per channel
-    if (rc) return rc;
+    DFK_CUDA(cudaStreamWaitEvent(st, ctx->join, 0));
     // fitters.py:407-417: every other buffer starts from its channel's buffer-0 result
-    return launch_lm(ctx, qi, nbuf, {1, 0}, N, guess_rows(rows, bpc * DFK_ROW_STRIDE, bpc, true), dc, opts, rows, st);
+    return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(rows, bpc * DFK_ROW_STRIDE, bpc, true), dc, opts, rows, st);
 }
 
 }  // namespace
@@ -573,6 +624,9 @@ int dfk_create(int device, dfk_ctx** out) {
     }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->consumed[i], cudaEventDisableTiming);
@@ -590,8 +644,9 @@ int dfk_destroy(dfk_ctx* ctx) {
     Guard g(ctx);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     DevBuf* bufs[] = {&ctx->qi, &ctx->dc, &ctx->retry, &ctx->counters, &ctx->slab[0], &ctx->slab[1],
-                      &ctx->rows, &ctx->stats, &ctx->misc};
+                      &ctx->rows, &ctx->stats, &ctx->misc, &ctx->qi_seed, &ctx->dc_seed};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (auto& kind : ctx->prof_ev)
@@ -602,8 +657,11 @@ int dfk_destroy(dfk_ctx* ctx) {
         if (ctx->copied[i]) cudaEventDestroy(ctx->copied[i]);
         if (ctx->consumed[i]) cudaEventDestroy(ctx->consumed[i]);
     }
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    if (ctx->join) cudaEventDestroy(ctx->join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
     return DFK_OK;
 }
@@ -645,7 +703,7 @@ int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, cons
     if (nbuf > 0 && (!qi_dev || !guess_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
     if (guess_stride != 0 && guess_stride < 4) return fail(DFK_ERR_ARG, "guess_stride must be 0 or >= 4");
     const dfk::GuessSrc gs = guess_stride == 0 ? guess_rows(guess_dev, 0, nbuf, false) : guess_rows(guess_dev, guess_stride, 1, false);
-    return launch_lm(ctx, qi_dev, nbuf, {1, 0}, N, gs, dc_dev, opts, rows_dev, ctx->stream());
+    return launch_lm(ctx, qi_dev, nbuf, {1, 0, 1}, N, gs, dc_dev, opts, rows_dev, ctx->stream());
 }
 
 int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
@@ -862,12 +920,12 @@ int dfk_profile_enable(dfk_ctx* ctx, int32_t on) {
     return DFK_OK;
 }
 
-int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int32_t reset) {
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[3], int64_t launches[3], int32_t reset) {
     DFK_ENTER(ctx);
     if (!ms_total || !launches) return fail(DFK_ERR_ARG, "null output pointer");
     const int rc = prof_drain(ctx);
     if (rc) return rc;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 3; ++k) {
         ms_total[k] = ctx->prof_ms[k];
         launches[k] = ctx->prof_n[k];
         if (reset) {

@@ -30,7 +30,8 @@ struct GuessSrc {
 };
 
 struct FitMap {
-    long long step, offset;
+    long long step, offset;  // unit u = f * step + offset indexes qi and dc
+    long long row_mul;       // its result row is rows[u * row_mul]  (1 unless qi is a compacted subset)
 };
 
 DFK_D void flush_counts(const LmCounts& c, LmCounts* global, bool leader) {
@@ -51,14 +52,16 @@ DFK_D void flush_counts(const LmCounts& c, LmCounts* global, bool leader) {
     }
 }
 
-template <int G, int MINB>
-__global__ void __launch_bounds__(kLmThreads, MINB) lm_first_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
+// TPB: threads per block.  Large batches use kLmThreads; a handful of fits (the cold seed fits that overlap the
+// demodulation) use one-warp blocks so that they spread over all SMs instead of loading a few of them.
+template <int G, int MINB, int TPB>
+__global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
                                                               int N, GuessSrc guess, const double* __restrict__ dc,
                                                               LmOpts o, double* rows,
                                                               int* __restrict__ retry_list, int* __restrict__ retry_count,
                                                               LmCounts* __restrict__ counts) {
     extern __shared__ double bes_smem[];
-    constexpr int kFitsPerBlock = kLmThreads / G;
+    constexpr int kFitsPerBlock = TPB / G;
     const int group = threadIdx.x / G;
     const int rank = threadIdx.x & (G - 1);
     double* bes = bes_smem + threadIdx.x;
@@ -80,13 +83,13 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_first_kernel(const double
         }
         int steps = 0;
         LmCounts local = {};
-        const double ssq = lm_descend<G>(N, q, 1, bes, kLmThreads, o, p, steps, local);
+        const double ssq = lm_descend<G>(N, q, 1, bes, TPB, o, p, steps, local);
         if (live) {
             cnt.n_state += local.n_state; cnt.n_ssq += local.n_ssq; cnt.n_solve += local.n_solve;
             cnt.n_bessel_steps += local.n_bessel_steps;
         }
         if (live && rank == 0) {
-            double* row = rows + u * kRowStride;
+            double* row = rows + u * map.row_mul * kRowStride;
             const bool done = ssq < o.fitok_threshold;
             if (done) normalise_params(p);
             row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_first_kernel(const double
 
 // retry_list holds unit indices (into qi and rows alike).
 __global__ void __launch_bounds__(kLmThreads) lm_retry_kernel(const double* __restrict__ qi, int N, LmOpts o,
-                                                              double* __restrict__ rows,
+                                                              long long row_mul, double* __restrict__ rows,
                                                               const int* __restrict__ retry_list,
                                                               const int* __restrict__ retry_count,
                                                               LmCounts* __restrict__ counts) {
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_retry_kernel(const double* __re
     LmCounts cnt = {};
     for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
         const long long f = retry_list[i];
-        double* row = rows + f * kRowStride;
+        double* row = rows + f * row_mul * kRowStride;
         const double* q = qi + f * 2 * N;
         double p[4] = {row[0], row[1], row[2], row[3]};
         double ssq = row[5];

@@ -170,10 +170,11 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
 int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset);
 /* Device-time accounting per kernel class for the roofline report: with profiling on, the NLS entry
  * points record CUDA event pairs on the launching stream around the demodulation launch (index 0) and
- * around the LM launches (index 1).  dfk_profile_read synchronises and returns the summed milliseconds
- * and the number of timed regions of each class. */
+ * around the LM launches (index 1), and on the side stream around the cold seed fits that overlap the
+ * demodulation (index 2).  dfk_profile_read synchronises and returns the summed milliseconds and the
+ * number of timed regions of each class. */
 int dfk_profile_enable(dfk_ctx* ctx, int32_t on);
-int dfk_profile_read(dfk_ctx* ctx, double ms_total[2], int64_t launches[2], int32_t reset);
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[3], int64_t launches[3], int32_t reset);
 /* Measured fp64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per thread, best of 3):
  * the denominator for the LM kernel's fraction of the FP64 roofline. */
 int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out);
