@@ -58,6 +58,7 @@ SYMBOLS = {
     "dfk_demod": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
     "dfk_lm_fit": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_nls_fit_seeded_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_batch_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
                                              ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
@@ -179,6 +180,11 @@ class Context:
         init_arr = (ctypes.c_double * 4)(*[float(v) for v in init])
         _check(self.lib, self.lib.dfk_nls_fit_dev(self._h, x_ptr, nbuf, R, N, w0, init_arr, int(bool(seeded)),
                                                   ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def nls_fit_seeded_dev(self, x_ptr, nbuf, R, N, w0, seed, opts, rows_ptr):
+        seed_arr = (ctypes.c_double * 4)(*[float(v) for v in seed])
+        _check(self.lib, self.lib.dfk_nls_fit_seeded_dev(self._h, x_ptr, nbuf, R, N, w0, seed_arr,
+                                                         ctypes.byref(opts) if opts is not None else None, rows_ptr))
 
     def nls_fit_batch_dev(self, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init, init_dev_ptr, init_stride, seeded,
                           opts, rows_ptr):

@@ -717,6 +717,18 @@ int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, 
                          ctx->stream());
 }
 
+int dfk_nls_fit_seeded_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
+                           const double seed[4], const dfk_lm_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    const int rc = check_nls_args(nbuf, R, N, w0);
+    if (rc) return rc;
+    if (!seed) return fail(DFK_ERR_ARG, "null seed");
+    if (nbuf > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    // every buffer is a warm start from the same 4 values: exactly the "seeded == 0" path with init = seed
+    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, seed, nullptr, 0, 0, nullptr, opts, rows_dev,
+                         ctx->stream());
+}
+
 int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t ld_c,
                           int64_t R, int32_t N, double w0, const double init[4], const double* init_dev,
                           int64_t init_stride, int32_t seeded, const dfk_lm_opts* opts, double* rows_dev) {

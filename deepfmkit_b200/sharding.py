@@ -57,3 +57,46 @@ def gather_rows(local_rows: np.ndarray, n_units: int, dst: int = 0, group=None):
         return None
     parts = [o.cpu().numpy()[: hi - lo] for o, (lo, hi) in zip(out, bounds)]
     return np.concatenate(parts, axis=0)
+
+
+def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, group=None, tunables_from=None):
+    """NLS readout of one long record sharded over the ranks of ``group`` as contiguous buffer-aligned slabs.
+
+    Every rank calls this with *its* slab: ``x_slab`` holds buffers ``slab_bounds(n_buffers_total, world, rank)``
+    of the record (a CUDA float64 tensor, or a numpy array that is copied to this rank's GPU).  Rank 0 fits
+    buffer 0 from ``init`` (fitters.py:404-405) inside its own slab; the fitted [amp, m, phi, psi] is broadcast
+    (32 bytes) and every other slab starts all its buffers from it (fitters.py:407-417).  No other exchange:
+    the kernels of different ranks never communicate.  Returns the full ``[n_buffers_total, 8]`` row table on
+    rank 0 (None elsewhere).
+    """
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from . import fit as fit_tunables
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = slab_bounds(n_buffers_total, world, rank)
+    nb = hi - lo
+    if device is None:
+        device = torch.cuda.current_device()
+    dev = torch.device("cuda", device)
+    xt = x_slab if isinstance(x_slab, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_slab, dtype=np.float64))
+    xt = xt.to(dev).contiguous().view(-1)
+    if xt.numel() < nb * R:
+        raise ValueError(f"rank {rank}: slab holds {xt.numel()} samples, needs {nb * R}")
+    ctx = _lib.get_context(device)
+    opts = fit_tunables.current_lm_opts(tunables_from)
+    rows = torch.zeros((nb, _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ctx.use_torch_stream()
+        try:
+            if rank == 0 and nb > 0:
+                ctx.nls_fit_dev(xt.data_ptr(), nb, R, ndata, w0, init, True, opts, rows.data_ptr())
+            torch.cuda.current_stream(dev).synchronize()
+            seed = broadcast_seed(rows[0, :4].cpu().numpy() if rank == 0 and nb > 0 else np.zeros(4), src=0, group=group)
+            if rank != 0 and nb > 0:
+                ctx.nls_fit_seeded_dev(xt.data_ptr(), nb, R, ndata, w0, seed, opts, rows.data_ptr())
+            torch.cuda.current_stream(dev).synchronize()
+        finally:
+            ctx.use_own_stream()
+    return gather_rows(rows.cpu().numpy(), n_buffers_total, dst=0, group=group)

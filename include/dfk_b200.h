@@ -113,6 +113,12 @@ int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, cons
 int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
                     const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
 
+/* A slab of a record whose buffer 0 lives elsewhere (another GPU): every buffer of the slab starts from
+ * seed[4], the fitted [amp, m, phi, psi] of the record's buffer 0 -- what each Pool chunk receives as
+ * seed_guess in fitters.py:407-417.  Slabs are independent: no inter-GPU traffic on the kernel path. */
+int dfk_nls_fit_seeded_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
+                           const double seed[4], const dfk_lm_opts* opts, double* rows_dev);
+
 /* The same for C channel records at once (additive API for multi-channel batches and Monte-Carlo
  * sweeps; the reference loops dff.fit(label) per channel, core.py:279-286).  Channel c is the
  * bufs_per_channel * R samples at x_dev + c * ld_c.  Cold starts use init[4], or, when init_dev is

@@ -481,3 +481,20 @@ def test_synth_statistics(torch_mod, ctx):
     a = x[:T].cpu().numpy()
     b = x[T:].cpu().numpy()
     assert abs(np.corrcoef(a - a.mean(), b - b.mean())[0, 1]) < 0.9  # different seeds per channel
+
+
+def test_single_record_sharded_over_gpus(torch_mod):
+    """One record cut into contiguous slabs over all visible GPUs (torchrun, nccl) == the one-GPU readout."""
+    import os
+    import subprocess
+    import sys
+    n = torch_mod.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    n = min(n, 4)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "multi", "sharded_record.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert f"SHARDED_OK world={n}" in out.stdout
