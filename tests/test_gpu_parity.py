@@ -498,3 +498,34 @@ def test_single_record_sharded_over_gpus(torch_mod):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert f"SHARDED_OK world={n}" in out.stdout
+
+
+def test_monte_carlo_sweep_reaches_crlb(torch_mod):
+    """Config-5 workload through the batched driver: device-generated realisations, per-m statistics.  The NLS fit
+    is efficient (notebook 1.1_CRLB-test): std(m_hat) sits on the reference's CRLB, the mean on the truth."""
+    from deepfmkit_b200 import crlb_sigma_m, nls_sweep
+    ms = [3.0, 6.0, 11.0, 17.0]
+    n_trials = 20000
+    out = nls_sweep(ms, n_trials, snr_db=40.0, ndata=15, seed=5, max_resident_bytes=48 << 20, return_rows=True)
+    assert out["rows"].shape == (4, n_trials, 8)
+    assert np.all(out["fitok"][:, 0] > 0.999)
+    # helpers.py:16-45 assumes an AC power of 0.5; 'snr' mode scales the noise to the record's actual AC power
+    # (physics.py:522-527), which depends on m -- put the bound on the same footing before comparing
+    ac_power = np.array([np.var(orc.snr_signal(m, 200e3, 1000.0, 1e-3, 300.0)) for m in ms])
+    ratio = out["m_std"] / (out["crlb_sigma_m"] * np.sqrt(ac_power / 0.5))
+    assert np.all((ratio > 0.96) & (ratio < 1.05)), ratio
+    assert np.all(np.abs(out["m_mean"] - np.array(ms)) < 5 * out["crlb_sigma_m"] / np.sqrt(n_trials) + 2e-5)
+    assert np.allclose(out["rows"][:, :, 1].std(axis=1), out["m_std"], rtol=1e-6)
+    assert np.allclose(out["crlb_sigma_m"], [orc.crlb_sigma_m(m, 15, 40.0, 200) for m in ms], rtol=1e-12)
+    # a handful of device-generated realisations re-fitted by the oracle: same rows within the gate
+    import torch
+    from deepfmkit_b200 import _lib
+    ctx = _lib.get_context(0)
+    x = torch.empty((3, 200), dtype=torch.float64, device="cuda")
+    ctx.synth_snr_slab_dev(x.data_ptr(), 200, 3, 200, 0, 200e3, 1000.0, 6.0, snr_db=40.0, seed=5 + 1 * n_trials)
+    ctx.synchronize()
+    xs = x.cpu().numpy()
+    for r in range(3):
+        ref = orc.nls_fit(xs[r], 200e3, 1000.0, 1, 15, init_m=6.0)[0]
+        got = out["rows"][1, r]
+        assert got[6] == ref[6] and np.max(np.abs(got[:4] - ref[:4])) < 1e-8
