@@ -255,6 +255,35 @@ int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid,
     return DFK_OK;
 }
 
+// One period per buffer (R == P <= 256, P % 4 == 0, no drift term): the quarter-wave kernel.  1 = launched, 0 = does not fit.
+int try_launch_period(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int32_t N, double* qi,
+                      double* dc, bool leave_room, cudaStream_t st) {
+    if (pl.periods != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || env_int("DFK_NO_PERIOD", 0))
+        return 0;
+    const int P = static_cast<int>(pl.P);
+    int nst = 12;
+    size_t smem = 0;
+    for (; nst >= 2; --nst) {
+        smem = dfk::period_smem_layout(P, N, nst).total;
+        if (smem <= static_cast<size_t>(ctx->max_smem_optin) - (leave_room ? seed_fit_reserve(N) : 0)) break;
+    }
+    if (nst < 2) return 0;
+    dfk::PeriodParams p;
+    p.x = x;
+    p.qi = qi;
+    p.dc = dc;
+    p.nbuf = nbuf;
+    p.P = P;
+    p.N = N;
+    p.nstages = nst;
+    const int64_t ngroups = (nbuf + dfk::kPeriodNbw - 1) / dfk::kPeriodNbw;
+    const int grid = static_cast<int>(std::min<int64_t>(ngroups, ctx->sm_count));
+    DFK_CUDA(cudaFuncSetAttribute(dfk::demod_period_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    dfk::demod_period_kernel<<<grid, dfk::kFoldThreads, smem, st>>>(p);
+    return 1;
+}
+
 // Short periods (P <= 256) with contiguous buffers: the barrier-free tile kernel.  Returns 1 if it launched,
 // 0 if the geometry does not fit it, < 0 on error.
 int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int64_t R, int32_t N,
@@ -321,7 +350,8 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
     int tiled = 0;
     if (pl.folded && aligned && ld_c == bpc * R) {
-        tiled = try_launch_tile(ctx, pl, x, nbuf, R, N, qi, dc, leave_room, st);
+        tiled = try_launch_period(ctx, pl, x, nbuf, N, qi, dc, leave_room, st);
+        if (tiled == 0) tiled = try_launch_tile(ctx, pl, x, nbuf, R, N, qi, dc, leave_room, st);
         if (tiled < 0) return tiled;
     }
     if (tiled) {

@@ -432,6 +432,38 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileP
         const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
         const int tot = nb * n;
         long long q = i * p.cpg;
+        if (!DRIFT && NBW > 1 && n == 1 && p.cpg == 1) {
+            // One period per buffer (the Monte-Carlo shape) and the whole group in one stage: nothing to fold.
+            // Lane j reads column j and P-j of all NBW rows and writes the combinations of column j for the NBW
+            // buffers as contiguous 128-bit stores -- the transpose the product below wants, with every shared
+            // memory access conflict-free.
+            const int stage = static_cast<int>(q % p.nstages);
+            const uint32_t phase = static_cast<uint32_t>((q / p.nstages) & 1);
+            while (*issued <= static_cast<unsigned long long>(q)) __nanosleep(64);
+            __threadfence_block();
+            mbar_wait(&full[stage], phase);
+            const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+            for (int j = lane; j <= half; j += 32) {
+                const bool self = (j == 0) || (j == half);
+                double a[NBW], b[NBW];
+#pragma unroll
+                for (int s = 0; s < NBW; ++s) {
+                    const bool have = s < nb;
+                    const double va = have ? sm[s * P + j] : 0.0;
+                    const double vb = (have && !self) ? sm[s * P + (P - j)] : 0.0;
+                    a[s] = va + vb;
+                    b[s] = self ? 0.0 : va - vb;
+                }
+                double2* xr = reinterpret_cast<double2*>(X + j * xrow);
+#pragma unroll
+                for (int s = 0; s < NBW; s += 2) {
+                    xr[s / 2] = make_double2(a[s], a[s + 1]);
+                    xr[(NBW + s) / 2] = make_double2(b[s], b[s + 1]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        } else {
         double2 accS[kTileMaxSlots], accT[kTileMaxSlots];
 #pragma unroll
         for (int s = 0; s < kTileMaxSlots; ++s) accS[s] = accT[s] = make_double2(0.0, 0.0);
@@ -497,6 +529,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileP
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
         }
+        }
 
         // outputs of the group: lane = output row (0 = mean, 1..N = Q_k, N+1..2N = I_k)
         for (int vb = 0; vb < NV; vb += 32) {
@@ -547,6 +580,236 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileP
                             p.dc[b] = val;
                         } else {
                             p.qi[b * static_cast<long long>(2 * N) + (v - 1)] = val;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// demod_period_kernel -- one modulation period per buffer (R = P <= 256, P % 4 == 0): the Monte-Carlo shape
+// (BASELINE config 5: 1.9e7 buffers of 1.6 kB).  Same CTA-wide ring and warp-owns-group scheme as the tile kernel
+// with groups of 8 buffers, but the product is cut down twice more, because here it -- not HBM -- is the bound
+// (the tile kernel's product keeps the shared-memory pipe > 90 % busy at this shape):
+//   * quarter-wave symmetry on top of the half-wave one: with j' = P/2 - j,
+//     cos(k th_j') = (-1)^k cos(k th_j) and sin(k th_j') = -(-1)^k sin(k th_j), so even and odd harmonics read
+//     different combinations (AE, AO, BE, BO) and the column range halves to 0..P/4;
+//   * every lane produces 2 output rows x 4 buffers (instead of 1 x 8), which loads 6 operands per 8 FMAs
+//     instead of 9: shared-memory loads are charged per lane-byte, broadcast or not.
+constexpr int kPeriodNbw = 8;
+
+struct PeriodParams {
+    const double* x;
+    double* qi;
+    double* dc;
+    long long nbuf;
+    int P, N;
+    int nstages;
+};
+
+struct PeriodSmem {
+    int quarter, nrows, xrow, stage_doubles;
+    size_t off_stage, off_t, off_x, off_rows, off_bar, total;
+    size_t x_per_warp;  // doubles
+};
+
+// output rows in the order cos-even (k = 0, 2, ..), cos-odd, sin-even, sin-odd, each block padded to an even count
+// so that a lane's two rows always read the same operand; total padded to a multiple of 32.
+inline __host__ __device__ int period_rows(int N) {
+    const int ce = N / 2 + 1, co = (N + 1) / 2, se = N / 2, so = (N + 1) / 2;
+    const int tot = (ce + (ce & 1)) + (co + (co & 1)) + (se + (se & 1)) + (so + (so & 1));
+    return (tot + 31) / 32 * 32;
+}
+
+inline __host__ __device__ PeriodSmem period_smem_layout(int P, int N, int nstages) {
+    PeriodSmem L;
+    L.quarter = P / 4;
+    L.nrows = period_rows(N);
+    L.xrow = 4 * kPeriodNbw + 2;
+    L.stage_doubles = kPeriodNbw * P;
+    L.x_per_warp = static_cast<size_t>(L.quarter + 1) * L.xrow;
+    size_t o = 0;
+    L.off_stage = o;
+    o += static_cast<size_t>(nstages) * L.stage_doubles * 8;
+    L.off_t = o;
+    o += static_cast<size_t>(L.quarter + 1) * L.nrows * 8;
+    L.off_x = o;
+    o += kFoldConsumerWarps * L.x_per_warp * 8;
+    L.off_rows = o;
+    o += static_cast<size_t>(L.nrows) * 2 * sizeof(int);  // row_type[], row_out[]
+    o = (o + 7) & ~static_cast<size_t>(7);
+    L.off_bar = o;
+    o += static_cast<size_t>(2 * nstages + 1) * 8;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const PeriodParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const PeriodSmem L = period_smem_layout(p.P, p.N, p.nstages);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
+    double* T = reinterpret_cast<double*>(smem_raw + L.off_t);
+    int* row_type = reinterpret_cast<int*>(smem_raw + L.off_rows);
+    int* row_out = row_type + L.nrows;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* empty = full + p.nstages;
+    volatile unsigned long long* issued = reinterpret_cast<volatile unsigned long long*>(empty + p.nstages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, N = p.N, half = P >> 1, quarter = L.quarter, nrows = L.nrows;
+    constexpr int NBW = kPeriodNbw;
+    const long long ngroups = (p.nbuf + NBW - 1) / NBW;
+    const long long my_groups = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        *issued = 0ull;
+        mbar_fence_init();
+        // row tables; row_out: -1 = padding, 0 = mean, k = Q_k (qi column k-1), N + k = I_k (qi column N+k-1)
+        int v = 0;
+        for (int type = 0; type < 4; ++type) {
+            const int k0 = (type == 0) ? 0 : (type == 2 ? 2 : 1);
+            int cnt = 0;
+            for (int k = k0; k <= N; k += 2, ++cnt, ++v) {
+                row_type[v] = type;
+                row_out[v] = type < 2 ? k : N + k;
+            }
+            if (cnt & 1) {
+                row_type[v] = type;
+                row_out[v] = -1;
+                ++v;
+            }
+        }
+        for (; v < nrows; ++v) {
+            row_type[v] = 3;
+            row_out[v] = -1;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (quarter + 1) * nrows; i += kFoldThreads) {
+        const int j = i / nrows, v = i - j * nrows;
+        const int out = row_out[v];
+        double val = 0.0;
+        if (out >= 0) {
+            const int k = out <= N ? out : out - N;
+            double sn, cs;
+            sincospi(2.0 * static_cast<double>((static_cast<long long>(k) * j) % P) / static_cast<double>(P), &sn, &cs);
+            val = out <= N ? cs : sn;
+        }
+        T[i] = val;
+    }
+    __syncthreads();
+
+    if (warp == kFoldConsumerWarps) {
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int stage = 0;
+            uint32_t phase = 0;
+            unsigned long long count = 0;
+            for (long long i = 0; i < my_groups; ++i) {
+                const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
+                const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+                const uint32_t bytes = static_cast<uint32_t>(nb) * static_cast<uint32_t>(P) * 8u;
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                bulk_load(stage_base + static_cast<size_t>(stage) * L.stage_doubles, p.x + b0 * static_cast<long long>(P),
+                          bytes, &full[stage], pol);
+                __threadfence_block();
+                *issued = ++count;
+                if (++stage == p.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    double* X = reinterpret_cast<double*>(smem_raw + L.off_x) + warp * L.x_per_warp;
+    const int xrow = L.xrow;
+    const double Rd = static_cast<double>(P);
+    for (long long i = warp; i < my_groups; i += kFoldConsumerWarps) {
+        const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
+        const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+        const int stage = static_cast<int>(i % p.nstages);
+        const uint32_t phase = static_cast<uint32_t>((i / p.nstages) & 1);
+        while (*issued <= static_cast<unsigned long long>(i)) __nanosleep(64);
+        __threadfence_block();
+        mbar_wait(&full[stage], phase);
+        const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+        // combinations of columns j, P-j, j' = P/2-j, P-j' for the NBW buffers of the group, written transposed
+        for (int j = lane; j <= quarter; j += 32) {
+            const int jp = half - j;
+            const bool first = j == 0, mid = j == quarter;
+            double2* xr = reinterpret_cast<double2*>(X + j * xrow);
+            double ae[NBW], ao[NBW], be[NBW], bo[NBW];
+#pragma unroll
+            for (int s = 0; s < NBW; ++s) {
+                const bool have = s < nb;
+                const double* row = sm + s * P;
+                const double s1 = have ? row[j] : 0.0;
+                const double s2 = (have && !first) ? row[P - j] : 0.0;
+                const double s3 = have ? row[jp] : 0.0;
+                const double s4 = (have && !first) ? row[half + j] : 0.0;  // column P - j'
+                const double aj = s1 + s2, bj = first ? 0.0 : s1 - s2;
+                const double ap = s3 + s4, bp = first ? 0.0 : s3 - s4;
+                ae[s] = mid ? aj : aj + ap;
+                ao[s] = mid ? 0.0 : aj - ap;
+                be[s] = mid ? 0.0 : bj - bp;
+                bo[s] = mid ? bj : bj + bp;
+            }
+#pragma unroll
+            for (int s = 0; s < NBW; s += 2) {
+                xr[(0 * NBW + s) / 2] = make_double2(ae[s], ae[s + 1]);
+                xr[(1 * NBW + s) / 2] = make_double2(ao[s], ao[s + 1]);
+                xr[(2 * NBW + s) / 2] = make_double2(be[s], be[s + 1]);
+                xr[(3 * NBW + s) / 2] = make_double2(bo[s], bo[s + 1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+
+        // product: lane -> rows (2i, 2i+1) of the 32-row block, buffers 4h..4h+3   (i = lane % 16, h = lane / 16)
+        const int pi = lane & 15, h = lane >> 4;
+        for (int vb = 0; vb < nrows; vb += 32) {
+            const int r0 = vb + 2 * pi;
+            const double* tp = T + r0;
+            const double* xp = X + row_type[r0] * NBW + 4 * h;
+            double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int j = 0; j <= quarter; ++j) {
+                const double2 t = *reinterpret_cast<const double2*>(tp + j * nrows);
+                const double2 xa = *reinterpret_cast<const double2*>(xp + j * xrow);
+                const double2 xb = *reinterpret_cast<const double2*>(xp + j * xrow + 2);
+                acc0[0] = fma(t.x, xa.x, acc0[0]);
+                acc0[1] = fma(t.x, xa.y, acc0[1]);
+                acc0[2] = fma(t.x, xb.x, acc0[2]);
+                acc0[3] = fma(t.x, xb.y, acc0[3]);
+                acc1[0] = fma(t.y, xa.x, acc1[0]);
+                acc1[1] = fma(t.y, xa.y, acc1[1]);
+                acc1[2] = fma(t.y, xb.x, acc1[2]);
+                acc1[3] = fma(t.y, xb.y, acc1[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int out = row_out[r0 + r];
+                if (out < 0) continue;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int slot = 4 * h + s;
+                    if (slot < nb) {
+                        const double val = (r == 0 ? acc0[s] : acc1[s]) / Rd;
+                        const long long b = b0 + slot;
+                        if (out == 0) {
+                            p.dc[b] = val;
+                        } else {
+                            p.qi[b * static_cast<long long>(2 * N) + (out - 1)] = val;
                         }
                     }
                 }

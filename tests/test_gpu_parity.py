@@ -123,10 +123,13 @@ def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
 
 
 @pytest.mark.parametrize("P,n,nh", [(2048, 3, 10), (1536, 2, 7), (1000, 1, 64), (6, 50, 2), (2, 40, 1), (256, 5, 31),
-                                    (258, 4, 16), (200, 3, 40), (2050, 2, 5), (75, 20, 10)])
+                                    (258, 4, 16), (200, 3, 40), (2050, 2, 5), (75, 20, 10),
+                                    (100, 1, 10), (256, 1, 31), (4, 1, 1), (8, 1, 3), (200, 1, 40), (202, 1, 10),
+                                    (12, 1, 5), (200, 1, 16)])
 def test_demod_period_and_harmonic_extremes(torch_mod, ctx, P, n, nh):
     """Largest folded period (2048), smallest (2), the tile/fold boundary (256/258), N = 1 and N = 64, a table too big
-    for the tile kernel (N = 40 at P = 200), and periods the fold cannot take (2050 > max, 75 odd)."""
+    for the tile kernel (N = 40 at P = 200), periods the fold cannot take (2050 > max, 75 odd), and one-period
+    buffers (n = 1) through the quarter-wave kernel (P % 4 == 0) or the tile kernel (P = 202)."""
     from deepfmkit_b200 import _lib
     f_mod = 1000.0
     f_samp = f_mod * P
