@@ -4,6 +4,8 @@ Gates (BASELINE.json north_star): demodulated I/Q within 1e-12 of the buffer's m
 m and amp within 1e-8 relative, phi and psi within 1e-8 rad on rows the reference fits (fitok 0/1);
 identical fitok flags everywhere.  EKF states within 1e-9 absolute of the reference loop.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -532,3 +534,38 @@ def test_monte_carlo_sweep_reaches_crlb(torch_mod):
         ref = orc.nls_fit(xs[r], 200e3, 1000.0, 1, 15, init_m=6.0)[0]
         got = out["rows"][1, r]
         assert got[6] == ref[6] and np.max(np.abs(got[:4] - ref[:4])) < 1e-8
+
+
+def _bulk_case(args):
+    m, snr, seed, init_m, phi0, psi0 = args
+    x = orc.snr_signal(m, 200e3, 1000.0, 2e-3, snr, seed=seed, phi0=phi0, psi0=psi0)
+    with np.errstate(all="ignore"):
+        row = orc.nls_fit(x, 200e3, 1000.0, 2, 12, init_m=init_m)[0]
+    return x, row
+
+
+def test_bulk_parity_over_random_cold_starts(torch_mod):
+    """1200 random single-buffer fits -- m in [2, 22], SNR 3..40 dB, random phases, half of them cold-started at
+    m = 6 so that the grid fallback and the failing branch are exercised at scale -- GPU batch vs oracle, one by one:
+    identical flags everywhere, parameters within the gate wherever the reference itself fits."""
+    from multiprocessing import Pool
+    from deepfmkit_b200 import nls_fit_batch
+    rng = np.random.RandomState(2024)
+    n = 1200
+    ms = rng.uniform(2.0, 22.0, n)
+    snrs = rng.choice([3.0, 10.0, 20.0, 40.0], n)
+    init_m = np.where(rng.rand(n) < 0.5, 6.0, ms)
+    phis, psis = rng.uniform(-3, 3, n), rng.uniform(-0.5, 0.5, n)
+    jobs = [(ms[i], snrs[i], 1000 + i, init_m[i], phis[i], psis[i]) for i in range(n)]
+    with Pool(min(16, os.cpu_count() or 1)) as pool:
+        res = pool.map(_bulk_case, jobs, chunksize=25)
+    x = np.stack([r[0] for r in res])
+    ref = np.stack([r[1] for r in res])
+    rows = nls_fit_batch(x, 200e3, 1000.0, 2, ndata=12, init_m=init_m, seeded=False)[:, 0, :]
+    flags_equal = rows[:, 6] == ref[:, 6]
+    assert {0.0, 1.0, 2.0} <= set(ref[:, 6]), "the sample must exercise all three flags"
+    assert np.all(flags_equal), (np.flatnonzero(~flags_equal), rows[~flags_equal, :7], ref[~flags_equal])
+    ok = ref[:, 6] < 2
+    err = np.abs(rows[ok, :4] - ref[ok, :4])
+    err[:, :2] /= np.abs(ref[ok, :2])
+    assert err.max() <= PARAM_TOL, (err.max(), np.unravel_index(err.argmax(), err.shape))
