@@ -412,11 +412,24 @@ DFK_HD void normalise_params(double* p) {
         p[1] = -p[1];
         p[2] += kPi;
     }
-    double r = fmod(p[2] + kPi, kTwoPi);
-    if (r != 0.0) {
-        if (r < 0.0) r += kTwoPi;
+    // (phi + pi) % (2 pi) - pi with Python's sign convention.  fmod is exact, and so are the two shortcuts: for
+    // t in [2 pi, 4 pi) the difference t - 2 pi is exact (Sterbenz), and for t in [-2 pi, 0) Python's own result
+    // is fmod's (t itself) plus 2 pi, rounded once.
+    const double t = p[2] + kPi;
+    double r;
+    if (t >= 0.0 && t < kTwoPi) {
+        r = t;
+    } else if (t >= kTwoPi && t < 2.0 * kTwoPi) {
+        r = t - kTwoPi;
+    } else if (t < 0.0 && t > -kTwoPi) {
+        r = t + kTwoPi;
     } else {
-        r = 0.0;
+        r = fmod(t, kTwoPi);
+        if (r != 0.0) {
+            if (r < 0.0) r += kTwoPi;
+        } else {
+            r = 0.0;
+        }
     }
     p[2] = r - kPi;
 }

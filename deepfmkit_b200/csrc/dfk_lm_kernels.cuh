@@ -103,6 +103,123 @@ __global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __res
     flush_counts(cnt, counts, rank == 0);
 }
 
+// Bulk variant of stage 1 for one thread per fit: the LM driver of fit.py:208-258 flattened into a per-lane state
+// machine.  Every trip of the loop does the same thing for every lane -- solve for the current damping, Miller
+// recurrence at the trial m, one model+Jacobian evaluation there, accept / reject bookkeeping -- and a lane whose
+// fit has ended takes the next fit at once, so the lanes of a warp stay busy although their fits need different
+// numbers of steps (in lm_first_kernel<1> only 21 of 32 lanes are active on average).  An accepted trial point is
+// where the reference recomputes coeffs (fit.py:250-251); evaluating the Jacobian with every trial makes that
+// second pass unnecessary.  The decisions (first strictly better damping of the fixed ladder, the stopping rule, the
+// step cap) are those of the reference, so flags and results agree with lm_first_kernel.
+// Normal equations of the current point live in shared memory (12 doubles per thread) to keep registers for the
+// evaluation.
+constexpr int kNeDoubles = 12;
+
+DFK_D void ne_store(double* s, const NormalEq& n, int stride) {
+    s[0 * stride] = n.a00; s[1 * stride] = n.a01; s[2 * stride] = n.a02; s[3 * stride] = n.a11;
+    s[4 * stride] = n.a12; s[5 * stride] = n.a22; s[6 * stride] = n.a33; s[7 * stride] = n.g0;
+    s[8 * stride] = n.g1; s[9 * stride] = n.g2; s[10 * stride] = n.g3; s[11 * stride] = n.ssq;
+}
+DFK_D void ne_load(const double* s, NormalEq& n, int stride) {
+    n.a00 = s[0 * stride]; n.a01 = s[1 * stride]; n.a02 = s[2 * stride]; n.a11 = s[3 * stride];
+    n.a12 = s[4 * stride]; n.a22 = s[5 * stride]; n.a33 = s[6 * stride]; n.g0 = s[7 * stride];
+    n.g1 = s[8 * stride]; n.g2 = s[9 * stride]; n.g3 = s[10 * stride]; n.ssq = s[11 * stride];
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
+                                                                   int N, GuessSrc guess, const double* __restrict__ dc,
+                                                                   LmOpts o, double* rows, int* __restrict__ retry_list,
+                                                                   int* __restrict__ retry_count,
+                                                                   LmCounts* __restrict__ counts) {
+    extern __shared__ double lm_smem[];
+    double* bes = lm_smem + threadIdx.x;                                   // (N + 2) x kLmThreads
+    double* nes = lm_smem + (N + 2) * kLmThreads + threadIdx.x;            // kNeDoubles x kLmThreads
+    const long long stride = static_cast<long long>(gridDim.x) * kLmThreads;
+    long long f = static_cast<long long>(blockIdx.x) * kLmThreads + threadIdx.x;
+    LmCounts cnt = {};
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    double ssq = 0.0;
+    const double* q = qi;
+    long long u = 0;
+    int lam = -1;  // -1: evaluate the starting point; 0..7: position in the damping ladder
+    int steps = 0;
+    bool active = false;
+    // fetch the first fit this lane has to do (skipping units that are already fitted)
+    auto fetch = [&]() {
+        active = false;
+        while (f < nfit) {
+            u = f * map.step + map.offset;
+            f += stride;
+            if (guess.skip_first && (u % guess.div) == 0) continue;
+            active = true;
+            break;
+        }
+        if (!active) return;
+        q = qi + u * 2 * N;
+        if (guess.ptr) {
+            const double* g = guess.ptr + (guess.div == 1 ? u : u / guess.div) * guess.stride;
+            p[0] = g[0]; p[1] = g[1]; p[2] = g[2]; p[3] = g[3];
+        } else {
+            p[0] = guess.val[0]; p[1] = guess.val[1]; p[2] = guess.val[2]; p[3] = guess.val[3];
+        }
+        lam = -1;
+        steps = 0;
+    };
+    fetch();
+    while (active) {
+        double dp[4] = {0.0, 0.0, 0.0, 0.0};
+        bool skip = false;
+        if (lam >= 0) {
+            NormalEq ne;
+            ne_load(nes, ne, kLmThreads);
+            damped_solve(ne, lambda_of(lam), dp);
+            cnt.n_solve++;
+            skip = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]) < 1e-15;  // fit.py:230
+        }
+        const double pt[4] = {p[0] + dp[0], p[1] + dp[1], p[2] + dp[2], p[3] + dp[3]};
+        NormalEq nt;
+        cnt.n_bessel_steps += skip ? 0 : bessel_j_upto(pt[1], N + 1, bes, kLmThreads);
+        eval_state<1>(N, q, 1, bes, kLmThreads, pt, nt);
+        bool finished = false;
+        if (lam < 0) {
+            cnt.n_state++;
+            ne_store(nes, nt, kLmThreads);
+            ssq = nt.ssq;
+            lam = 0;
+            finished = o.max_steps <= 0;
+        } else {
+            if (!skip) cnt.n_ssq++;
+            if (!skip && nt.ssq < ssq) {  // first strictly better damping wins (fit.py:240-243)
+                const double moved = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]);
+                p[0] = pt[0]; p[1] = pt[1]; p[2] = pt[2]; p[3] = pt[3];
+                ne_store(nes, nt, kLmThreads);
+                ssq = nt.ssq;
+                cnt.n_state++;
+                ++steps;
+                // fit.py:255 compares the accepted ssq with its own recomputation: 0 < conv_improve unless it is <= 0
+                finished = ((0.0 < o.conv_improve) && moved < o.conv_param) || steps >= o.max_steps;
+                lam = 0;
+            } else if (++lam == 8) {
+                finished = true;  // no damping improved (fit.py:246)
+            }
+        }
+        if (finished) {
+            double* row = rows + u * map.row_mul * kRowStride;
+            const bool done = ssq < o.fitok_threshold;
+            if (done) normalise_params(p);
+            row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
+            row[4] = dc ? dc[u] : 0.0;
+            row[5] = ssq;
+            row[6] = done ? 0.0 : -1.0;
+            row[7] = static_cast<double>(steps);
+            if (!done) retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
+            fetch();
+        }
+    }
+    flush_counts(cnt, counts, true);
+}
+
 // retry_list holds unit indices (into qi and rows alike).
 __global__ void __launch_bounds__(kLmThreads) lm_retry_kernel(const double* __restrict__ qi, int N, LmOpts o,
                                                               long long row_mul, double* __restrict__ rows,
