@@ -26,7 +26,6 @@ constexpr int kFoldConsumerWarps = 8;
 constexpr int kFoldConsumers = kFoldConsumerWarps * 32;  // 256
 constexpr int kFoldThreads = kFoldConsumers + 32;        // + producer warp
 constexpr int kFoldStageBytes = 16384;
-constexpr int kFoldMaxSlots = static_cast<int>(kMaxFoldPeriod / 2 / kFoldConsumers);  // column pairs per thread (4)
 
 struct FoldParams {
     const double* x;
