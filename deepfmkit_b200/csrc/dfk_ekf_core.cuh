@@ -36,14 +36,15 @@ struct EkfConsts {
 };
 
 // Sample index k is absolute: unlike the NLS lock-in, the EKF phase never restarts (fitters.py:280).
-DFK_HD void ekf_step(EkfState& s, double z, long long k, const EkfConsts& c) {
+// kd: the absolute sample index as a double (exact for every index below 2^53).
+DFK_HD void ekf_step(EkfState& s, double z, double kd, const EkfConsts& c) {
 #pragma unroll
     for (int i = 0; i < 5; ++i) s.P[i][i] += c.q[i];  // P = F P F^T + Q with F = I (fitters.py:276)
 
     const double a = s.x[0], m = s.x[1], phi = s.x[2], psi = s.x[3], dc = s.x[4];
     // the angle is formed exactly as numpy does, w_m * (k / f_samp) + psi, each operation rounded once:
     // at t ~ 100 s its rounding (1e-10 rad) is the largest noise term the filter sees from arithmetic.
-    const double t = static_cast<double>(k) / c.f_samp;
+    const double t = kd / c.f_samp;
     const double theta = add_rn(mul_rn(c.w_m, t), psi);
     double st, ct;
     sincos_hd(theta, &st, &ct);

@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const double* __restri
     double nxt[kEkfPrefetch];
 #pragma unroll
     for (int i = 0; i < kEkfPrefetch; ++i) nxt[i] = (i < T) ? __ldg(zc + i * ld_t) : 0.0;
-    long long next_snap = R;  // snapshot after sample index next_snap - 1
+    long long until_snap = R;  // samples left before the next state snapshot
+    long long snaps = 0;
+    double kd = static_cast<double>(a.k0);  // absolute sample index, exact in a double
     for (long long t0 = 0; t0 < T; t0 += kEkfPrefetch) {
 #pragma unroll
         for (int i = 0; i < kEkfPrefetch; ++i) stage[i][threadIdx.x] = nxt[i];
@@ -115,16 +117,16 @@ __global__ void __launch_bounds__(kEkfThreads) ekf_kernel(const double* __restri
         const int lim = (T - t0 < kEkfPrefetch) ? static_cast<int>(T - t0) : kEkfPrefetch;
 #pragma unroll 1
         for (int i = 0; i < lim; ++i) {
-            const long long t = t0 + i;
-            ekf_step(s, stage[i][threadIdx.x], a.k0 + t, k);
-            if (t + 1 == next_snap) {
-                const long long idx = next_snap / R - 1;
-                if (idx < nbuf) {
-                    double* row = out + idx * 8;
+            ekf_step(s, stage[i][threadIdx.x], kd, k);
+            kd += 1.0;
+            if (--until_snap == 0) {
+                if (snaps < nbuf) {
+                    double* row = out + snaps * 8;
                     row[0] = s.x[0]; row[1] = s.x[1]; row[2] = s.x[2]; row[3] = s.x[3]; row[4] = s.x[4];
                     row[5] = 0.0; row[6] = 1.0; row[7] = 0.0;  // ssq = 0, fitok = 1 (fitters.py:313-318)
                 }
-                next_snap += R;
+                ++snaps;
+                until_snap = R;
             }
         }
     }

@@ -99,7 +99,7 @@ void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, 
     c.r = r_val;
     const int64_t nbuf = T / R;
     for (int64_t k = 0; k < T; ++k) {
-        ekf_step(s, z[k], k, c);
+        ekf_step(s, z[k], static_cast<double>(k), c);
         if ((k + 1) % R == 0) {
             const int64_t idx = (k + 1) / R - 1;
             if (idx < nbuf) std::memcpy(rows + idx * 5, s.x, 5 * sizeof(double));
