@@ -258,7 +258,7 @@ int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid,
 // One period per buffer (R == P <= 256, P % 4 == 0, no drift term): the quarter-wave kernel.  1 = launched, 0 = does not fit.
 int try_launch_period(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int32_t N, double* qi,
                       double* dc, bool leave_room, cudaStream_t st) {
-    if (pl.periods != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || env_int("DFK_NO_PERIOD", 0))
+    if (pl.periods != 1 || pl.kmul != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || env_int("DFK_NO_PERIOD", 0))
         return 0;
     const int P = static_cast<int>(pl.P);
     int nst = 12;
@@ -313,6 +313,7 @@ int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int
     p.P = P;
     p.periods = n;
     p.N = N;
+    p.kmul = pl.kmul;
     p.pps = pps;
     p.cpg = (nbw * n + pps - 1) / pps;
     p.nstages = nst;
@@ -368,6 +369,7 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
         p.P = static_cast<int>(pl.P);
         p.periods = static_cast<int>(pl.periods);
         p.N = N;
+        p.kmul = pl.kmul;
         p.pps = g.pps;
         p.nstages = g.nstages;
         for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];

@@ -35,6 +35,7 @@ struct FoldParams {
     long long bpc;   // buffers per channel record
     long long ld_c;  // samples between the starts of consecutive channel records
     int R, P, periods, N;
+    int kmul;     // modulation periods per fold length P (harmonic k of f_mod = harmonic kmul*k of the fold)
     int pps;      // periods per pipeline stage
     int nstages;  // ring depth
     double delta[kMaxHarmonics];
@@ -105,13 +106,13 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
     // for every buffer because the lock-in phase restarts at each buffer.
     for (int i = tid; i < (N + 1) * 32; i += kFoldThreads) {
         const int k = i >> 5, l = i & 31;
-        const long long r = (static_cast<long long>(k) * l) % P;
+        const long long r = (static_cast<long long>(k) * p.kmul * l) % P;
         double s, c;
         sincospi(2.0 * static_cast<double>(r) / static_cast<double>(P), &s, &c);
         sm_tw[i] = make_double2(c, s);
     }
     for (int k = tid; k <= N; k += kFoldThreads) {
-        const long long r = (static_cast<long long>(k) * 32) % P;
+        const long long r = (static_cast<long long>(k) * p.kmul * 32) % P;
         double s, c;
         sincospi(2.0 * static_cast<double>(r) / static_cast<double>(P), &s, &c);
         sm_step[k] = make_double2(c, s);
@@ -296,6 +297,7 @@ struct TileParams {
     double* dc;
     long long nbuf;
     int R, P, periods, N;
+    int kmul;     // modulation periods per fold length P
     int pps;      // periods per ring stage
     int cpg;      // stages per full group
     int nstages;  // ring depth
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileP
         if (v < NV && j <= half) {
             const int k = v <= N ? v : v - N;
             double sn, cs;
-            sincospi(2.0 * static_cast<double>((static_cast<long long>(k) * j) % P) / static_cast<double>(P), &sn, &cs);
+            sincospi(2.0 * static_cast<double>((static_cast<long long>(k) * p.kmul * j) % P) / static_cast<double>(P), &sn, &cs);
             a = v <= N ? cs : sn;
             if (DRIFT && v > 0) b = v <= N ? -p.delta[k - 1] * sn : p.delta[k - 1] * cs;
         }

@@ -25,12 +25,14 @@ namespace dfk {
 constexpr int kMaxHarmonics = 64;
 constexpr int64_t kMaxFoldPeriod = 2048;  // 256 consumer threads x 4 column pairs
 constexpr double kDriftRamp = 4e-13;
+constexpr int kMaxFoldMul = 16;
 
 struct DemodPlan {
-    bool folded;     // integer even period -> folded TMA kernel; else general kernel
+    bool folded;     // a whole even fold length exists -> folded TMA kernels; else the direct kernel
     bool drift;      // apply the first-order frequency-offset term
-    int64_t P;       // samples per modulation period (folded only)
+    int64_t P;       // fold length in samples: kmul modulation periods (folded only)
     int64_t periods; // R / P
+    int kmul;        // modulation periods per fold length: harmonic k of f_mod is harmonic kmul*k of the fold
     double delta[kMaxHarmonics];  // w_k - 2*pi*(k+1)/P, evaluated in double-double
 };
 
@@ -48,21 +50,38 @@ inline DemodPlan make_demod_plan(int64_t R, double w0, int N) {
     pl.drift = false;
     pl.P = 0;
     pl.periods = 0;
+    pl.kmul = 1;
     for (int k = 0; k < kMaxHarmonics; ++k) pl.delta[k] = 0.0;
     if (!(w0 > 0.0) || R <= 0 || N <= 0 || N > kMaxHarmonics) return pl;
     const double two_pi_hi = 6.283185307179586, two_pi_lo = 2.4492935982947064e-16;
-    const double pf = std::nearbyint(two_pi_hi / w0);
-    if (!(pf >= 2.0) || pf > static_cast<double>(kMaxFoldPeriod)) return pl;
+    // The fold length is the smallest whole EVEN number of samples that holds a whole number q of modulation
+    // periods (q = 1 for the BASELINE configs; q = 2 for an odd period such as the reference's own 30 kHz / 400 Hz
+    // record, P = 75 -> fold 150; q up to kMaxFoldMul covers rational periods like 162.5 samples).  Harmonic k of
+    // the modulation is then harmonic q*k of the fold, which only changes which twiddles the kernels tabulate.
+    double pf = 0.0;
+    int q = 0;
+    for (int cand = 1; cand <= kMaxFoldMul; ++cand) {
+        const double c = std::nearbyint(static_cast<double>(cand) * two_pi_hi / w0);
+        if (!(c >= 2.0)) continue;
+        if (c > static_cast<double>(kMaxFoldPeriod)) break;
+        if (std::fabs(w0 * c - static_cast<double>(cand) * two_pi_hi) > 1e-12 * cand * two_pi_hi) continue;
+        const int64_t ci = static_cast<int64_t>(c);
+        if ((ci & 1) || (R % ci) != 0) continue;
+        pf = c;
+        q = cand;
+        break;
+    }
+    if (q == 0) return pl;
     const int64_t P = static_cast<int64_t>(pf);
-    if ((P & 1) || (R % P) != 0) return pl;
-    if (std::fabs(w0 * pf - two_pi_hi) > 1e-12 * two_pi_hi) return pl;
+    const double qd = static_cast<double>(q);
     double worst = 0.0;
     for (int k = 0; k < N; ++k) {
         const double kf = static_cast<double>(k + 1);
         const double wk = kf * w0;  // what Python computes for (n + 1) * w0
-        // wk * P and 2*pi*(k+1), each as an unevaluated sum hi + lo
+        // wk * P and 2*pi*q*(k+1), each as an unevaluated sum hi + lo
+        const double kq = kf * qd;
         const double a_hi = wk * pf, a_lo = std::fma(wk, pf, -a_hi);
-        const double b_hi = kf * two_pi_hi, b_lo = std::fma(kf, two_pi_hi, -b_hi) + kf * two_pi_lo;
+        const double b_hi = kq * two_pi_hi, b_lo = std::fma(kq, two_pi_hi, -b_hi) + kq * two_pi_lo;
         pl.delta[k] = ((a_hi - b_hi) + (a_lo - b_lo)) / pf;
         const double ramp = std::fabs(pl.delta[k]) * static_cast<double>(R);
         if (ramp > worst) worst = ramp;
@@ -70,6 +89,7 @@ inline DemodPlan make_demod_plan(int64_t R, double w0, int N) {
     pl.folded = true;
     pl.P = P;
     pl.periods = R / P;
+    pl.kmul = q;
     pl.drift = worst > kDriftRamp;
     return pl;
 }

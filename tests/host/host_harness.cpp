@@ -109,6 +109,8 @@ void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, 
 
 // Demod plan (host logic shared with the CUDA launcher) and a scalar emulation of the folded
 // kernel's arithmetic: fold over periods, rotation recurrence from the unit-circle table, drift term.
+int hh_demod_plan_mul(int64_t R, double w0, int N) { return make_demod_plan(R, w0, N).kmul; }
+
 int hh_demod_plan(int64_t R, double w0, int N, int64_t* P, int* use_drift, double* delta /*N*/) {
     DemodPlan pl = make_demod_plan(R, w0, N);
     *P = pl.P;
@@ -140,13 +142,14 @@ void hh_demod_fold_emulate(const double* x, int64_t R, int N, double w0, int for
     for (int k0 = 0; k0 < N; k0 += KB) {
         std::vector<double> cs(KB, 0.0), ss(KB, 0.0), cu(KB, 0.0), su(KB, 0.0);
         for (int64_t j = 0; j < P; ++j) {
-            const int64_t r0 = (static_cast<int64_t>(k0 + 1) * j) % P;  // block start from the table
+            const int64_t r0 = (static_cast<int64_t>(k0 + 1) * pl.kmul * j) % P;  // block start from the table
+            const int64_t rs = (static_cast<int64_t>(pl.kmul) * j) % P;           // one harmonic further
             double c = wc[r0], s = ws[r0];
             for (int kk = 0; kk < KB; ++kk) {
                 cs[kk] += S[j] * c; ss[kk] += S[j] * s;
                 cu[kk] += U[j] * c; su[kk] += U[j] * s;
-                const double cn = c * wc[j] - s * ws[j];
-                s = s * wc[j] + c * ws[j];
+                const double cn = c * wc[rs] - s * ws[rs];
+                s = s * wc[rs] + c * ws[rs];
                 c = cn;
             }
         }

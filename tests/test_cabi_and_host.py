@@ -79,7 +79,8 @@ def test_demod_plan_selection(lib):
     assert _lib.demod_path(4000, w(200e3, 1000.0)) == 1
     assert _lib.demod_path(20000, w(1e6, 1000.0)) == 1
     assert _lib.demod_path(200, w(200e3, 1000.0)) == 1
-    assert _lib.demod_path(1500, w(30e3, 400.0)) == 0      # 75 samples per period: odd
+    assert _lib.demod_path(1500, w(30e3, 400.0)) == 1      # 75 samples per period: folds at 150 (two periods)
+    assert _lib.demod_path(75, w(30e3, 400.0)) == 0        # a single odd period per buffer cannot fold
     assert _lib.demod_path(3240, w(200e3, 1234.5)) == 0    # non-integer period
     assert _lib.demod_path(4100, w(200e3, 1000.0)) == 0    # buffer is not a whole number of periods
 

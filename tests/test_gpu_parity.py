@@ -90,9 +90,10 @@ def test_demod_folded_vs_reference(torch_mod, ctx, golden, name):
 
 
 @pytest.mark.parametrize("f_samp,f_mod,n,nh", [(200e3, 1234.5, 20, 10), (201e3, 1000.0, 20, 10), (48e3, 440.0, 7, 13),
-                                               (200e3, 1000.0, 1, 15)])
+                                               (200e3, 1000.0, 1, 15), (30e3, 400.0, 20, 10), (162.5e3, 1000.0, 20, 10)])
 def test_demod_vs_oracle_general(torch_mod, ctx, f_samp, f_mod, n, nh):
-    """Non-integer / odd periods go through the direct kernel; n = 1 (cfg 5) through the folded one."""
+    """Incommensurate periods go through the direct kernel; odd (201, 75: the reference's own 30 kHz / 400 Hz record)
+    and rational (162.5) periods fold over two or four periods; n = 1 (cfg 5) takes the single-period kernel."""
     x = orc.snr_signal(6.0, f_samp, f_mod, 0.05, 40.0, seed=3)
     R, _, nbuf = orc.buffer_geometry(len(x), f_samp, f_mod, n)
     w0 = orc.rad_per_sample(f_samp, f_mod)
@@ -127,7 +128,7 @@ def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
 @pytest.mark.parametrize("P,n,nh", [(2048, 3, 10), (1536, 2, 7), (1000, 1, 64), (6, 50, 2), (2, 40, 1), (256, 5, 31),
                                     (258, 4, 16), (200, 3, 40), (2050, 2, 5), (75, 20, 10),
                                     (100, 1, 10), (256, 1, 31), (4, 1, 1), (8, 1, 3), (200, 1, 40), (202, 1, 10),
-                                    (12, 1, 5), (200, 1, 16)])
+                                    (12, 1, 5), (200, 1, 16), (75, 1, 10), (333, 6, 12), (1001, 2, 9)])
 def test_demod_period_and_harmonic_extremes(torch_mod, ctx, P, n, nh):
     """Largest folded period (2048), smallest (2), the tile/fold boundary (256/258), N = 1 and N = 64, a table too big
     for the tile kernel (N = 40 at P = 200), periods the fold cannot take (2050 > max, 75 odd), and one-period
@@ -137,7 +138,8 @@ def test_demod_period_and_harmonic_extremes(torch_mod, ctx, P, n, nh):
     f_samp = f_mod * P
     R = P * n
     w0 = orc.rad_per_sample(f_samp, f_mod)
-    assert _lib.demod_path(R, w0) == (1 if (P % 2 == 0 and P <= 2048) else 0)
+    folds = (P % 2 == 0 and P <= 2048) or (P % 2 == 1 and n % 2 == 0 and 2 * P <= 2048)
+    assert _lib.demod_path(R, w0) == (1 if folds else 0)
     rng = np.random.RandomState(P + n)
     nbuf = 37
     t = np.arange(nbuf * R)

@@ -221,13 +221,40 @@ def test_fold_demod_arithmetic(hh, golden, name, plan_drift, tol_plan):
             assert abs(dc.value - g["rows_seq"][b, 4]) <= 1e-14 * abs(g["rows_seq"][b, 4])
 
 
-def test_demod_plan_rejects_non_integer_period(hh):
+def test_demod_plan_fold_lengths(hh):
+    """Even period: one period per fold.  Odd or rational period: the smallest even whole number of samples that
+    holds whole periods (the reference's own record, 30 kHz / 400 Hz = 75 samples, folds at 150).  Otherwise, or if
+    the buffer is not a whole number of folds: no fold (direct kernel)."""
     P = ctypes.c_int64()
     drift = ctypes.c_int()
     delta = np.zeros(10)
-    w0 = orc.rad_per_sample(200e3, 1234.5)
-    assert hh.hh_demod_plan(ctypes.c_int64(3240), ctypes.c_double(w0), ctypes.c_int(10), ctypes.byref(P),
-                            ctypes.byref(drift), _ptr(delta)) == 0
-    w0 = orc.rad_per_sample(201e3, 1000.0)  # odd period
-    assert hh.hh_demod_plan(ctypes.c_int64(4020), ctypes.c_double(w0), ctypes.c_int(10), ctypes.byref(P),
-                            ctypes.byref(drift), _ptr(delta)) == 0
+
+    def plan(R, f_samp, f_mod):
+        w0 = orc.rad_per_sample(f_samp, f_mod)
+        ok = hh.hh_demod_plan(ctypes.c_int64(R), ctypes.c_double(w0), ctypes.c_int(10), ctypes.byref(P),
+                              ctypes.byref(drift), _ptr(delta))
+        return ok, P.value, hh.hh_demod_plan_mul(ctypes.c_int64(R), ctypes.c_double(w0), ctypes.c_int(10))
+
+    assert plan(4000, 200e3, 1000.0) == (1, 200, 1)
+    assert plan(1500, 30e3, 400.0) == (1, 150, 2)        # odd period
+    assert plan(4020, 201e3, 1000.0) == (1, 402, 2)
+    assert plan(3250, 162.5e3, 1000.0) == (1, 650, 4)    # 162.5 samples per period
+    assert plan(3240, 200e3, 1234.5)[0] == 0             # incommensurate
+    assert plan(4100, 200e3, 1000.0)[0] == 0             # buffer is not a whole number of periods
+    assert plan(75, 30e3, 400.0)[0] == 0                 # one odd period per buffer: no even fold fits
+    assert plan(80000, 4e6, 1000.0)[0] == 0              # 4000 samples per period: longer than the kernels fold
+
+
+@pytest.mark.parametrize("f_samp,f_mod,n,nh", [(30e3, 400.0, 20, 10), (162.5e3, 1000.0, 20, 8)])
+def test_fold_emulation_odd_and_rational_periods(hh, f_samp, f_mod, n, nh):
+    x = orc.snr_signal(6.0, f_samp, f_mod, 0.2, 40.0, seed=9)
+    R, _, nbuf = orc.buffer_geometry(len(x), f_samp, f_mod, n)
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    for b in range(2):
+        buf = np.ascontiguousarray(x[b * R:(b + 1) * R])
+        qi = np.zeros(2 * nh)
+        dc = ctypes.c_double()
+        hh.hh_demod_fold_emulate(_ptr(buf), ctypes.c_int64(R), ctypes.c_int(nh), ctypes.c_double(w0),
+                                 ctypes.c_int(-1), _ptr(qi), ctypes.byref(dc))
+        ref = orc.lockin_means(buf, w0, nh)
+        assert np.max(np.abs(qi - ref)) <= 3e-13 * np.abs(ref).max()
