@@ -66,7 +66,7 @@ typedef struct dfk_ekf_opts {
 typedef struct dfk_lm_counters {
     uint64_t n_state;   /* model+Jacobian evaluations  (fit.py:68  coeffs)  */
     uint64_t n_ssq;     /* residual-only evaluations   (fit.py:152 ssqf)    */
-    uint64_t n_solve;   /* damped 4x4 solves           (fit.py:169 msolve)  */
+    uint64_t n_solve;   /* damped normal-equation solves (fit.py:169 msolve) */
     uint64_t n_grid;    /* grid-search fallbacks       (fit.py:260)         */
     uint64_t n_bessel_steps; /* Miller recurrence steps over all evaluations */
 } dfk_lm_counters;
@@ -77,7 +77,7 @@ typedef struct dfk_ctx dfk_ctx;
 int dfk_abi_version(void);
 const char* dfk_last_error(void);
 int dfk_device_count(void);
-/* One context per (thread, device): owns two streams, pinned staging and device scratch. */
+/* One context per (thread, device): owns its streams (compute, copy, side) and device scratch. */
 int dfk_create(int device, dfk_ctx** out);
 int dfk_destroy(dfk_ctx* ctx);
 /* Use a caller-owned stream (e.g. torch's current stream) for the device-pointer calls;
@@ -186,7 +186,8 @@ int dfk_profile_read(dfk_ctx* ctx, double ms_total[3], int64_t launches[3], int3
 int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out);
 /* Kernel launches issued through this context since creation (bench.py's gpu_launches). */
 int64_t dfk_launch_count(dfk_ctx* ctx);
-/* Which demod kernel the given geometry selects: 1 = folded TMA kernel, 0 = general kernel. */
+/* Which demod path the given geometry selects: 1 = a folded TMA kernel (fold / tile / single-period),
+ * 0 = the direct kernel (incommensurate period or a buffer that is not a whole number of fold lengths). */
 int dfk_demod_path(int64_t R, double w0);
 /* Bessel J_0..J_nmax(x) by the device's Miller recurrence, evaluated on the device (testing). */
 int dfk_bessel_dev(dfk_ctx* ctx, const double* x_dev, int64_t n, int32_t nmax, double* out_dev);
