@@ -183,3 +183,54 @@ def test_bench_reference_arm_contract():
     ref = orc.nls_fit(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, schedule="seeded", n_chunks=2)
     assert np.array_equal(rows, ref)
     assert bench.NBUF == 180000 and bench.R == 20000
+
+
+def test_reference_facade_dispatches_to_b200_fitters(lib, tmp_path):
+    """INTEGRATION.md section 1 on the real thing: the unmodified reference (when its checkout is present, i.e. in the
+    build container) with its two fitter classes swapped for ours.  The facade reaches our C ABI: here, without a
+    GPU, that shows as the library's loud 'no CUDA device' error; the frame-level parity of the same call is what
+    `-m gpu` tests check against fixtures minted from this very reference."""
+    ref = os.environ.get("DFK_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present on this machine")
+    from unittest.mock import MagicMock
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors",
+                                             "matplotlib.dates", "matplotlib.cm", "pyplnoise")}
+    for name in saved:
+        sys.modules[name] = MagicMock()
+    os.symlink(ref, tmp_path / "DeepFMKit")
+    sys.path.insert(0, str(tmp_path))
+    old_dont_write = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        import DeepFMKit.core as core
+        import deepfmkit_b200 as b2
+        from deepfmkit_b200 import _lib
+        core.StandardNLSFitter, core.EKFFitter = b2.StandardNLSFitter, b2.EKFFitter
+        dff = core.DeepFitFramework()
+        laser = core.LaserConfig(label="l")
+        laser.f_mod = 1000
+        ifo = core.InterferometerConfig(label="i")
+        core.set_laser_df_for_effect(laser, ifo, 6.0)
+        sim = core.DFMIObject(label="ch", laser_config=laser, ifo_config=ifo, f_samp=200e3)
+        dff.load_sim(sim)
+        dff.simulate(main_label="ch", n_seconds=0.1, mode="snr", snr_db=40)
+        if _lib.device_count() == 0:
+            for method in ("nls", "ekf"):
+                with pytest.raises(RuntimeError, match="no CUDA device"):
+                    dff.fit("ch", method=method, verbose=False)
+        else:
+            fobj = dff.fit("ch", parallel=True)
+            assert list(dff.fits_df["ch_nls"].columns) == ["amp", "m", "phi", "psi", "dc", "ssq", "fitok", "tau"]
+            assert fobj.nbuf == 5 and abs(fobj.m.mean() - 6.0) < 1e-2
+    finally:
+        sys.dont_write_bytecode = old_dont_write
+        sys.path.remove(str(tmp_path))
+        for k in list(sys.modules):
+            if k == "DeepFMKit" or k.startswith("DeepFMKit."):
+                del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
