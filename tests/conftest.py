@@ -13,6 +13,8 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CPU oracle is fanned out over a fork pool in a few tests; torch's threads make Python warn about it
+    config.addinivalue_line("filterwarnings", "ignore:This process .* is multi-threaded:DeprecationWarning")
 
 
 def load_golden(name):

@@ -319,6 +319,38 @@ def test_ekf_batch_layouts_agree(torch_mod, golden):
     assert np.max(np.abs(a[0, :, :5] - ref[:, :5])) < 1e-9
 
 
+def _ekf_case(args):
+    x, kw = args
+    return orc.ekf_track(x, 200e3, 1000.0, 20, **kw)
+
+
+def test_ekf_random_settings_vs_oracle(torch_mod, ctx):
+    """Eight channels with random true parameters, SNR, initial guesses, P0, Q and R through dfk_ekf_dev one call per
+    setting (options are per call), each against the oracle loop over the same 12000 samples."""
+    from multiprocessing import Pool
+    from deepfmkit_b200 import _lib
+    rng = np.random.RandomState(77)
+    jobs, opts_list = [], []
+    for c in range(8):
+        x = orc.snr_signal(rng.uniform(3, 12), 200e3, 1000.0, 0.06, rng.choice([20.0, 40.0]), seed=200 + c,
+                           phi0=rng.uniform(-3, 3), psi0=rng.uniform(-0.3, 0.3))
+        kw = dict(init_a=rng.uniform(0.8, 2.0), init_m=rng.uniform(4, 10), init_phi=rng.uniform(-1, 1),
+                  init_psi=rng.uniform(-0.2, 0.2), p0_diag=rng.uniform(0.1, 2.0, 5), q_diag=10.0 ** rng.uniform(-9, -5, 5),
+                  r_val=None if c % 2 else float(10.0 ** rng.uniform(-5, -2)))
+        jobs.append((x, kw))
+    with Pool(8) as pool:
+        refs = pool.map(_ekf_case, jobs)
+    for (x, kw), ref in zip(jobs, refs):
+        o = _lib.default_ekf_opts()
+        o.init[0], o.init[1], o.init[2], o.init[3] = kw["init_a"], kw["init_m"], kw["init_phi"], kw["init_psi"]
+        for i in range(5):
+            o.p0_diag[i], o.q_diag[i] = kw["p0_diag"][i], kw["q_diag"][i]
+        o.r_val = float("nan") if kw["r_val"] is None else kw["r_val"]
+        rows = ctx.ekf_host(x[None, :], 4000, 200e3, 1000.0, o)[0]
+        scale = np.maximum(np.abs(ref[:, :5]), 1.0)
+        assert np.max(np.abs(rows[:, :5] - ref[:, :5]) / scale) < 1e-9, kw
+
+
 def test_ekf_slabwise_equals_whole_record(torch_mod, ctx, golden):
     """dfk_ekf_stream_dev over three slabs with carried state == one pass over the record (same initial dc and R)."""
     from deepfmkit_b200 import _lib
