@@ -88,11 +88,12 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("DFK_LIB_PATH", LIB_PATH)  # development: A/B two builds of the library
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(deepfmkit_b200 has no CPU fallback)")
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (restype, argtypes) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype = restype
