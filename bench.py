@@ -157,6 +157,54 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ---- CPU leg for the other BASELINE configs (bounded samples; `--impl reference --workload cfgN`) -------------------
+def _cfg5_job(job):
+    from oracle import dfmi_oracle as orc
+    m, seed = job
+    x = orc.snr_signal(float(m), 200e3, 1000.0, 1e-3, 40.0, seed=seed)
+    return orc.nls_fit(x, 200e3, 1000.0, 1, 15, init_m=float(m))[0]
+
+
+def run_reference_workload(args):
+    """The oracle port of the reference on a bounded sample of cfg 1, 3, 4 or 5 (cfg 2 is the default arm)."""
+    from multiprocessing import Pool
+    from oracle import dfmi_oracle as orc
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    cores = host_cores()
+    cfg = args.workload
+    if cfg in ("cfg1", "cfg3"):
+        secs = 10.0 if cfg == "cfg1" else 20.0
+        x = orc.snr_signal(6.0, 200e3, 1000.0, secs, 40.0, seed=0)
+        t0 = time.perf_counter()
+        rows = orc.nls_fit_pool(x, 200e3, 1000.0, 20, 10, n_procs=cores)
+        dt = time.perf_counter() - t0
+        out = {"metric": METRIC, "value": len(rows) / dt, "unit": UNIT, "cores": cores,
+               "sample": f"1 channel x {secs:.0f} s ({len(rows)} buffers of 4000 samples), Pool schedule, start-up included"}
+    elif cfg == "cfg5":
+        jobs = [(m, s) for m in range(2, 21) for s in range(100)]
+        t0 = time.perf_counter()
+        with Pool(cores) as pool:
+            rows = pool.map(_cfg5_job, jobs, chunksize=25)
+        dt = time.perf_counter() - t0
+        out = {"metric": "single_buffer_fits_per_sec", "value": len(rows) / dt, "unit": "fits/s", "cores": cores,
+               "sample": f"{len(jobs)} realisations (100 per m in 2..20), Pool over realisations, signal synthesis "
+                         "included as in workers.py:132-189"}
+    elif cfg == "cfg4":
+        x = orc.snr_signal(6.0, 200e3, 1000.0, 0.1, 40.0, seed=0)
+        t0 = time.perf_counter()
+        orc.ekf_track(x, 200e3, 1000.0, 20)
+        dt = time.perf_counter() - t0
+        out = {"metric": "ekf_samples_per_sec", "value": len(x) / dt, "unit": "samples/s", "cores": 1,
+               "sample": "1 channel x 0.1 s (20000 steps) on one core; channels are independent, a box scales this by "
+                         f"its core count ({cores} here)"}
+    else:
+        raise SystemExit(f"unknown workload {cfg}")
+    out.update({"impl": "reference", "kind": "port", "workload": cfg})
+    emit(out)
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU schedule (fitters.py:395-428: buffer 0, then a process pool over
     chunks of the rest) restated by the oracle, on all host cores, each step a bounded sample of cfg 2."""
@@ -350,11 +398,13 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="reference arm only: which BASELINE config's bounded CPU sample to time (default: the contract's cfg2)")
     args = ap.parse_args()
     if args.steps < 1 or args.warmup < 0:
         raise SystemExit("--steps must be >= 1 and --warmup >= 0")
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args) if args.workload == "cfg2" else run_reference_workload(args)
     return run_gpu(args)
 
 

@@ -5,7 +5,8 @@
 
 Geometries follow BASELINE.json's configs; records that do not fit one GPU are cut to a resident wave
 (stated in the output).  Everything is generated on the device; times are CUDA events on the launching
-stream, best-of-reps after one warm-up.  One JSON line per config.
+stream, best-of-reps after one warm-up.  One JSON line per config.  (The CPU baseline beside each config is
+`python bench.py --impl reference --workload cfgN`: only bench.py's CPU leg may run the oracle.)
 """
 import argparse
 import json
@@ -124,56 +125,11 @@ def ekf_case(ctx, name, channels, seconds, reps, time_major, note="", start_s=0.
     print(json.dumps(out), flush=True)
 
 
-# ---- CPU baselines beside each config: the oracle port of the reference on the host cores, bounded samples ------
-def _cfg5_job(args):
-    from oracle import dfmi_oracle as orc
-    m, seed = args
-    x = orc.snr_signal(float(m), 200e3, 1000.0, 1e-3, 40.0, seed=seed)
-    return orc.nls_fit(x, 200e3, 1000.0, 1, 15, init_m=float(m))[0]
-
-
-def cpu_baseline(cfg):
-    import time
-    from multiprocessing import Pool
-    from oracle import dfmi_oracle as orc
-    cores = len(os.sched_getaffinity(0))
-    if cfg in ("cfg1", "cfg3"):
-        secs = 10.0 if cfg == "cfg1" else 20.0
-        x = orc.snr_signal(6.0, 200e3, 1000.0, secs, 40.0, seed=0)
-        t0 = time.perf_counter()
-        rows = orc.nls_fit_pool(x, 200e3, 1000.0, 20, 10, n_procs=cores)
-        dt = time.perf_counter() - t0
-        return {"kind": "port", "cores": cores, "sample": f"1 channel x {secs:.0f} s ({len(rows)} buffers), Pool schedule",
-                "buffers_per_s": len(rows) / dt, "samples_per_s": len(rows) * 4000 / dt}
-    if cfg == "cfg5":
-        jobs = [(m, s) for m in range(2, 21) for s in range(100)]
-        t0 = time.perf_counter()
-        with Pool(cores) as pool:
-            rows = pool.map(_cfg5_job, jobs, chunksize=25)
-        dt = time.perf_counter() - t0
-        return {"kind": "port", "cores": cores, "sample": f"{len(jobs)} realisations (100 per m), Pool over realisations, "
-                "signal synthesis included as in workers.py:132-189", "fits_per_s": len(rows) / dt}
-    if cfg == "cfg4":
-        x = orc.snr_signal(6.0, 200e3, 1000.0, 0.1, 40.0, seed=0)
-        t0 = time.perf_counter()
-        orc.ekf_track(x, 200e3, 1000.0, 20)
-        dt = time.perf_counter() - t0
-        return {"kind": "port", "cores": 1, "sample": "1 channel x 0.1 s (20000 steps); channels are independent, so "
-                "the box scales this by its core count", "samples_per_s": len(x) / dt, "host_cores": cores}
-    return None
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle port on a bounded sample of each config")
     args = ap.parse_args()
-    if args.cpu:
-        for c in args.configs:
-            base = cpu_baseline(c)
-            if base:
-                print(json.dumps({"config": c, "cpu_baseline": base}), flush=True)
     ctx = _lib.Context(0)
     ctx.use_torch_stream()
     for c in args.configs:

@@ -64,13 +64,24 @@ def test_no_gpu_means_loud_failure(lib):
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "deepfmkit_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
-                assert "scipy" not in text or f == "dfk_bessel.cuh", f
+    """Only tests/, smoke() and bench.py's CPU legs may touch oracle/: not the package, not the dev tools."""
+    for sub in ("deepfmkit_b200", "benchmarks", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                    assert "dfmi_oracle" not in text, f
+                    if sub == "deepfmkit_b200":
+                        assert "scipy" not in text or f == "dfk_bessel.cuh", f
+
+
+def test_missing_library_is_a_loud_error(monkeypatch):
+    from deepfmkit_b200 import _lib
+    monkeypatch.setenv("DFK_LIB_PATH", os.path.join(ROOT, "deepfmkit_b200", "no_such_library.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError, match="is missing"):
+        _lib.load_library()
 
 
 def test_demod_plan_selection(lib):
