@@ -235,6 +235,31 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank to the CPUs of its GPU's NUMA node before it allocates pinned host memory, so that the e2e leg's
+    host record is first-touched on the socket the GPU hangs off (matters once several ranks stream at once)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ---- GPU arm --------------------------------------------------------------------------------------------
 def run_gpu(args):
     import numpy as np
@@ -250,6 +275,7 @@ def run_gpu(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -362,7 +388,8 @@ def run_gpu(args):
                                        "oracle port of the reference's Pool schedule, pool start-up included"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_nbuf * R * 8,
                     "d2h_bytes_per_step": e2e_nbuf * _lib.ROW_STRIDE * 8, "ms_per_step": float(te.item()) * 1e3,
-                    "buffers_per_gpu": e2e_nbuf, "api": "dfk_nls_fit_host (StandardNLSFitter.fit), pinned host record"},
+                    "buffers_per_gpu": e2e_nbuf, "api": "dfk_nls_fit_host (StandardNLSFitter.fit), pinned host record",
+                    "rank0_numa_node": numa_node},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
