@@ -452,9 +452,14 @@ int launch_flat(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, i
 template <int G>
 int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
                  const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
-    switch (env_int("DFK_LM_MINB", 4)) {  // development override: resident blocks per SM the kernel is compiled for
-        case 6: return launch_first_b<G, 6, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
-        case 8: return launch_first_b<G, 8, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+    // 128 registers give 4 resident blocks per SM; the 96-register build (5 per SM, a few spills) is ~10 % slower
+    // per fit but wins when it saves a whole wave of a small batch (cfg 2: 1407 blocks = 3 waves of 592 or 2 of 740)
+    const int64_t blocks = (nfit + (dfk::kLmThreads / G) - 1) / (dfk::kLmThreads / G);
+    const int64_t w4 = (blocks + 4 * ctx->sm_count - 1) / (4 * ctx->sm_count);
+    const int64_t w5 = (blocks + 5 * ctx->sm_count - 1) / (5 * ctx->sm_count);
+    const int minb = env_int("DFK_LM_MINB", (w5 < w4 && w5 <= 3) ? 5 : 4);
+    switch (minb) {
+        case 5: return launch_first_b<G, 5, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
         default: return launch_first_b<G, 4, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
     }
 }
