@@ -358,7 +358,14 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_nbuf / float(te.item())
     assert np.array_equal(rows_h[:1024, 6], head[:1024, 6])
-    del xh, xh_np
+    # the same call on ordinary (pageable) memory -- what a numpy array out of pandas is -- on a tenth of the record
+    pg_nbuf = max(1000, e2e_nbuf // 10)
+    x_pg = np.array(xh_np[: pg_nbuf * R])
+    ctx.nls_fit_host(x_pg, R, NDATA, w0, INIT, seeded=True, opts=opts)
+    t0 = time.perf_counter()
+    ctx.nls_fit_host(x_pg, R, NDATA, w0, INIT, seeded=True, opts=opts)
+    pg_value = pg_nbuf / (time.perf_counter() - t0)
+    del xh, xh_np, x_pg
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -389,7 +396,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_nbuf * R * 8,
                     "d2h_bytes_per_step": e2e_nbuf * _lib.ROW_STRIDE * 8, "ms_per_step": float(te.item()) * 1e3,
                     "buffers_per_gpu": e2e_nbuf, "api": "dfk_nls_fit_host (StandardNLSFitter.fit), pinned host record",
-                    "rank0_numa_node": numa_node},
+                    "rank0_numa_node": numa_node,
+                    "pageable_input": {"value": pg_value, "unit": UNIT, "buffers": pg_nbuf,
+                                       "note": "rank 0, unpinned numpy input staged by copy threads through pinned buffers"}},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "dfk_demod.cuh"
 #include "dfk_ekf_kernels.cuh"
@@ -53,6 +55,11 @@ struct dfk_ctx {
     bool use_user = false;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;
+    // pageable host records are staged through pinned buffers filled by a few copy threads
+    static constexpr int kStagers = 3;
+    static constexpr size_t kStageBytes = 64u << 20;
+    void* stager[kStagers] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
     DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc, qi_seed, dc_seed;
     int64_t launches = 0;
     // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the
@@ -521,6 +528,57 @@ int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int
     return DFK_OK;
 }
 
+bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = static_cast<int>(std::min<size_t>(hw ? std::min(hw, 16u) : 4u, bytes / (4u << 20) + 1));
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t chunk = ((bytes / nt) + 4095) & ~static_cast<size_t>(4095);
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, chunk * t), hi = std::min(bytes, chunk * (t + 1));
+        if (hi > lo)
+            pool.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// Host -> device copy of one slab on the copy stream.  Pinned (or registered) memory goes by DMA directly; pageable
+// memory -- what a numpy array from pandas is -- would make cudaMemcpyAsync stage it synchronously at ~10 GB/s, so
+// it is copied by a few threads into pinned staging buffers whose DMA overlaps the next buffer's fill.
+int copy_slab_to_device(dfk_ctx* ctx, void* dst, const void* src, size_t bytes, bool pageable) {
+    if (!pageable) {
+        DFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        return DFK_OK;
+    }
+    for (int i = 0; i < dfk_ctx::kStagers; ++i) {
+        if (!ctx->stager[i]) {
+            DFK_CUDA(cudaHostAlloc(&ctx->stager[i], dfk_ctx::kStageBytes, cudaHostAllocDefault));
+            DFK_CUDA(cudaEventCreateWithFlags(&ctx->stager_free[i], cudaEventDisableTiming));
+        }
+    }
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += dfk_ctx::kStageBytes, k = (k + 1) % dfk_ctx::kStagers) {
+        const size_t n = std::min(dfk_ctx::kStageBytes, bytes - off);
+        DFK_CUDA(cudaEventSynchronize(ctx->stager_free[k]));  // (a never-recorded event counts as complete)
+        parallel_memcpy(ctx->stager[k], static_cast<const char*>(src) + off, n);
+        DFK_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->stager[k], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        DFK_CUDA(cudaEventRecord(ctx->stager_free[k], ctx->copy_stream));
+    }
+    return DFK_OK;
+}
+
 int check_nls_args(int64_t nbuf, int64_t R, int32_t N, double w0) {
     if (nbuf < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry: nbuf=%lld R=%lld", (long long)nbuf, (long long)R);
     if (N < 1 || N > DFK_MAX_HARMONICS) return fail(DFK_ERR_ARG, "harmonic count %d outside 1..%d", N, DFK_MAX_HARMONICS);
@@ -714,6 +772,10 @@ int dfk_destroy(dfk_ctx* ctx) {
         if (ctx->copied[i]) cudaEventDestroy(ctx->copied[i]);
         if (ctx->consumed[i]) cudaEventDestroy(ctx->consumed[i]);
     }
+    for (int i = 0; i < dfk_ctx::kStagers; ++i) {
+        if (ctx->stager[i]) cudaFreeHost(ctx->stager[i]);
+        if (ctx->stager_free[i]) cudaEventDestroy(ctx->stager_free[i]);
+    }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
     if (ctx->join) cudaEventDestroy(ctx->join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -832,14 +894,15 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
     if (rc) return rc;
     double* rows = static_cast<double*>(ctx->rows.ptr);
     cudaStream_t st = ctx->stream();
+    const bool pageable = is_pageable(x_host);
     int64_t done = 0;
     for (int64_t i = 0; done < nbuf; ++i) {
         const int sl = static_cast<int>(i & 1);
         const int64_t nb = std::min(slab_buffers, nbuf - done);
         double* dst = static_cast<double*>(ctx->slab[sl].ptr);
         if (i >= 2) DFK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->consumed[sl], 0));
-        DFK_CUDA(cudaMemcpyAsync(dst, x_host + done * R, static_cast<size_t>(nb) * R * 8, cudaMemcpyHostToDevice,
-                                 ctx->copy_stream));
+        rc = copy_slab_to_device(ctx, dst, x_host + done * R, static_cast<size_t>(nb) * R * 8, pageable);
+        if (rc) return rc;
         DFK_CUDA(cudaEventRecord(ctx->copied[sl], ctx->copy_stream));
         DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[sl], 0));
         rc = nls_on_device(ctx, dst, 1, nb, nb * R, R, N, w0, init, nullptr, 0, seeded,
