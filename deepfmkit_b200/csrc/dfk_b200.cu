@@ -977,7 +977,10 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
     rc = ensure(ctx, ctx->rows, std::max<size_t>(8, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8));
     if (rc) return rc;
     cudaStream_t st = ctx->stream();
-    DFK_CUDA(cudaMemcpyAsync(ctx->slab[0].ptr, z_host, static_cast<size_t>(T) * C * 8, cudaMemcpyHostToDevice, st));
+    rc = copy_slab_to_device(ctx, ctx->slab[0].ptr, z_host, static_cast<size_t>(T) * C * 8, is_pageable(z_host));
+    if (rc) return rc;
+    DFK_CUDA(cudaEventRecord(ctx->copied[0], ctx->copy_stream));
+    DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[0], 0));
     rc = dfk_ekf_dev(ctx, static_cast<const double*>(ctx->slab[0].ptr), T, C, 1, T, R, f_samp, f_mod, opts,
                      static_cast<double*>(ctx->rows.ptr));
     if (rc) return rc;
