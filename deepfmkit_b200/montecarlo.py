@@ -73,7 +73,7 @@ def crlb_sigma_m(m_true: float, ndata: int, snr_db: float, buffer_size: int) -> 
 
 def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, ndata=15, init_a=1.6, init_m=None,
               amp=1.0, visibility=1.0, phi0=0.0, psi0=0.0, seed=0, device=0, max_resident_bytes=8 << 30,
-              tunables_from=None, return_rows=False):
+              tunables_from=None, return_rows=False, _seed_stride=None, _raw_stats=False):
     """Fit ``n_trials`` independent single-buffer realisations at every m in ``m_values``.
 
     init_m: None -> each realisation starts from its true m (workers.py:167-173); a float -> the same cold start
@@ -90,6 +90,7 @@ def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, 
     w0 = 2.0 * np.pi * f_mod / f_samp
     opts = fit_tunables.current_lm_opts(tunables_from)
     per_wave = max(1, min(int(n_trials), int(max_resident_bytes // (len(ms) * R * 8))))
+    seed_stride = int(n_trials) if _seed_stride is None else int(_seed_stride)
     stats = {k: [] for k in ("sum", "sumsq", "min", "max", "worst", "ok", "ssq")}
     all_rows = [] if return_rows else None
     with torch.cuda.device(dev):
@@ -106,7 +107,7 @@ def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, 
                 nw = min(per_wave, n_trials - done)
                 for i, m in enumerate(ms):  # one generator launch per grid point: realisation = "channel" = seed
                     ctx.synth_snr_slab_dev(x[i].data_ptr(), R, nw, R, 0, f_samp, f_mod, float(m), amp, visibility, phi0,
-                                           0.0, psi0, snr_db, seed + done + i * int(n_trials))
+                                           0.0, psi0, snr_db, seed + done + i * seed_stride)
                 xv, rv, gv = x[:, :nw], rows[:, :nw], guess[:, :nw]
                 if nw != per_wave:
                     xv, rv, gv = xv.contiguous(), rv.contiguous(), gv.contiguous()
@@ -126,23 +127,71 @@ def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, 
             torch.cuda.current_stream(dev).synchronize()
         finally:
             ctx.use_own_stream()
-    nt = float(n_trials)
-    total = torch.stack(stats["sum"]).sum(0).cpu().numpy()
-    sq = torch.stack(stats["sumsq"]).sum(0).cpu().numpy()
+    part = {"n": int(n_trials), "truth": truth.cpu().numpy(),
+            "sum": torch.stack(stats["sum"]).sum(0).cpu().numpy(), "sumsq": torch.stack(stats["sumsq"]).sum(0).cpu().numpy(),
+            "min": torch.stack(stats["min"]).min(0).values.cpu().numpy(),
+            "max": torch.stack(stats["max"]).max(0).values.cpu().numpy(),
+            "worst": torch.stack(stats["worst"]).max(0).values.cpu().numpy(),
+            "ok": torch.stack(stats["ok"]).sum(0).cpu().numpy().astype(np.float64),
+            "ssq": torch.stack(stats["ssq"]).sum(0).cpu().numpy()}
+    if _raw_stats:
+        return part
+    out = _combine_partials(ms, [part], ndata, snr_db, R)
+    if return_rows:
+        out["rows"] = np.concatenate(all_rows, axis=1)
+    return out
+
+
+def nls_sweep_sharded(m_values, n_trials, group=None, device=None, seed=0, **kwargs):
+    """``nls_sweep`` with the realisations split over the ranks of a ``torch.distributed`` group (one process per GPU).
+
+    Realisations are independent, so the split is by realisation index: rank r draws trials
+    ``slab_bounds(n_trials, world, r)`` with its own disjoint seed range and nothing crosses the GPUs but the per-m
+    sufficient statistics at the end (a few hundred bytes, gathered as Python objects).  Every rank returns the
+    combined result; ``return_rows`` is not supported here.
+    """
+    import torch
+    import torch.distributed as dist
+    from .sharding import slab_bounds
+
+    if kwargs.pop("return_rows", False):
+        raise ValueError("return_rows is a single-GPU option")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = slab_bounds(int(n_trials), world, rank)
+    if device is None:
+        device = torch.cuda.current_device()
+    ms = np.atleast_1d(np.asarray(m_values, dtype=np.float64))
+    part = None
+    if hi > lo:
+        # the seed of realisation t of grid point i must not depend on the split: nls_sweep uses
+        # seed + done + i * n_trials with `done` counting from 0, so shift by lo and keep the per-m stride global
+        part = _sweep_partial(ms, hi - lo, seed + lo, int(n_trials), device, **kwargs)
+    parts = [None] * world
+    dist.all_gather_object(parts, part, group=group)
+    return _combine_partials(ms, [p for p in parts if p is not None], kwargs.get("ndata", 15), kwargs.get("snr_db", 40.0),
+                             int(kwargs.get("f_samp", 200e3) / kwargs.get("f_mod", 1000.0) * kwargs.get("n", 1)))
+
+
+def _sweep_partial(ms, n_local, seed0, seed_stride, device, **kwargs):
+    """Sufficient statistics of n_local realisations per m (numpy, host)."""
+    out = nls_sweep(ms, n_local, seed=seed0, device=device, _seed_stride=seed_stride, _raw_stats=True, **kwargs)
+    return out
+
+
+def _combine_partials(ms, parts, ndata, snr_db, R):
+    nt = float(sum(p["n"] for p in parts))
+    total = sum(p["sum"] for p in parts)
+    sq = sum(p["sumsq"] for p in parts)
     mean = total / nt
-    tr = truth.cpu().numpy()
-    # std about the sample mean from the second moment about the truth (avoids cancellation at high SNR)
+    tr = parts[0]["truth"]
     var = np.maximum(sq / nt - (mean - tr) ** 2, 0.0)
-    out = {"m_values": ms, "n_trials": int(n_trials),
-           "fitok": torch.stack(stats["ok"]).sum(0).cpu().numpy() / nt,
-           "ssq_mean": torch.stack(stats["ssq"]).sum(0).cpu().numpy() / nt,
+    out = {"m_values": ms, "n_trials": int(nt), "fitok": sum(p["ok"] for p in parts) / nt,
+           "ssq_mean": sum(p["ssq"] for p in parts) / nt,
            "crlb_sigma_m": np.array([crlb_sigma_m(m, ndata, snr_db, R) for m in ms])}
-    mn = torch.stack(stats["min"]).min(0).values.cpu().numpy()
-    mx = torch.stack(stats["max"]).max(0).values.cpu().numpy()
-    worst = torch.stack(stats["worst"]).max(0).values.cpu().numpy()
+    mn = np.min([p["min"] for p in parts], axis=0)
+    mx = np.max([p["max"] for p in parts], axis=0)
+    worst = np.max([p["worst"] for p in parts], axis=0)
     for c, name in enumerate(("amp", "m", "phi", "psi")):
         out[f"{name}_mean"], out[f"{name}_std"] = mean[:, c], np.sqrt(var[:, c])
         out[f"{name}_min"], out[f"{name}_max"], out[f"{name}_worst"] = mn[:, c], mx[:, c], worst[:, c]
-    if return_rows:
-        out["rows"] = np.concatenate(all_rows, axis=1)
     return out

@@ -522,9 +522,11 @@ def test_synth_statistics(torch_mod, ctx):
     assert abs(np.corrcoef(a - a.mean(), b - b.mean())[0, 1]) < 0.9  # different seeds per channel
 
 
-def test_single_record_sharded_over_gpus(torch_mod):
-    """One record cut into contiguous slabs over all visible GPUs (torchrun, nccl) == the one-GPU readout."""
-    import os
+@pytest.mark.parametrize("script,token,port", [("sharded_record.py", "SHARDED_OK", 29577),
+                                               ("sharded_sweep.py", "SWEEP_OK", 29578)])
+def test_sharded_over_gpus(torch_mod, script, token, port):
+    """One record cut into contiguous slabs / one Monte-Carlo sweep split by realisation over all visible GPUs
+    (torchrun, nccl) == the one-GPU result."""
     import subprocess
     import sys
     n = torch_mod.cuda.device_count()
@@ -533,10 +535,10 @@ def test_single_record_sharded_over_gpus(torch_mod):
     n = min(n, 4)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tests", "multi", "sharded_record.py")]
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "multi", script)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert f"SHARDED_OK world={n}" in out.stdout
+    assert f"{token} world={n}" in out.stdout
 
 
 def test_monte_carlo_sweep_reaches_crlb(torch_mod):
