@@ -100,3 +100,30 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
         finally:
             ctx.use_own_stream()
     return gather_rows(rows.cpu().numpy(), n_buffers_total, dst=0, group=group)
+
+
+def ekf_fit_sharded(z_channels, n_channels_total, f_samp, f_mod, n, device=None, group=None, **ekf_kwargs):
+    """EKF over many channels split over the ranks by channel (time is sequential, channels are independent).
+
+    Every rank passes the records of *its* channels ``slab_bounds(n_channels_total, world, rank)`` as ``[C_local, T]``;
+    rank 0 gets the ``[n_channels_total, nbuf, 8]`` table, the others None.  No exchange but the final gather.
+    """
+    import torch
+    import torch.distributed as dist
+    from .fitters import ekf_fit_batch
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lo, hi = slab_bounds(n_channels_total, world, rank)
+    if device is None:
+        device = torch.cuda.current_device()
+    z = np.atleast_2d(np.asarray(z_channels, dtype=np.float64)) if not isinstance(z_channels, torch.Tensor) else z_channels
+    if z.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank}: got {z.shape[0]} channels, owns {hi - lo}")
+    rows = ekf_fit_batch(z, f_samp, f_mod, n, device=device, **ekf_kwargs) if hi > lo else np.zeros((0, 0, 8))
+    nbuf = rows.shape[1] if hi > lo else 0
+    sizes = [None] * world
+    dist.all_gather_object(sizes, nbuf, group=group)
+    nbuf = max(sizes)
+    flat = rows.reshape(hi - lo, nbuf * 8) if hi > lo else np.zeros((0, nbuf * 8))
+    table = gather_rows(flat, n_channels_total, dst=0, group=group)
+    return None if table is None else table.reshape(n_channels_total, nbuf, 8)

@@ -12,7 +12,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from deepfmkit_b200 import _lib  # noqa: E402
-from deepfmkit_b200.sharding import nls_fit_sharded, slab_bounds  # noqa: E402
+from deepfmkit_b200.sharding import ekf_fit_sharded, nls_fit_sharded, slab_bounds  # noqa: E402
 from oracle import dfmi_oracle as orc  # noqa: E402
 
 
@@ -36,6 +36,15 @@ def main():
         ref = orc.nls_fit(x, f_samp, f_mod, n, nh, schedule="gpu")
         assert np.array_equal(rows[:, 6], ref[:, 6])
         assert np.max(np.abs(rows[:, :4] - ref[:, :4])) < 1e-8
+    # EKF: 5 channels split by channel over the ranks == the one-GPU batch
+    from deepfmkit_b200 import ekf_fit_batch
+    chans = np.stack([orc.snr_signal(6.0, f_samp, f_mod, 0.06, 40.0, seed=40 + c, phi0=0.3 * c) for c in range(5)])
+    clo, chi = slab_bounds(5, world, rank)
+    table = ekf_fit_sharded(chans[clo:chi], 5, f_samp, f_mod, n, device=local)
+    if rank == 0:
+        assert np.array_equal(table, ekf_fit_batch(chans, f_samp, f_mod, n, device=local))
+        ref = orc.ekf_track(chans[4], f_samp, f_mod, n)
+        assert np.max(np.abs(table[4, :, :5] - ref[:, :5])) < 1e-9
         print(f"SHARDED_OK world={world} nbuf={nbuf}")
     dist.barrier()
     dist.destroy_process_group()
