@@ -525,6 +525,16 @@ int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int
     dfk::lm_retry_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, N, o, map.row_mul, rows, list, count, counters);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
+    if (nfit >= dfk::kFlatRetryMin) {  // enough fits that many may be parked: the thread-per-fit retry kernel stands by
+        const size_t fsmem = static_cast<size_t>(N + 2 + dfk::kNeDoubles) * dfk::kLmThreads * sizeof(double);
+        DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(fsmem)));
+        const int fgrid = static_cast<int>(std::min<int64_t>((nfit + dfk::kLmThreads - 1) / dfk::kLmThreads,
+                                                             static_cast<int64_t>(ctx->sm_count) * 3));
+        dfk::lm_retry_flat_kernel<<<fgrid, dfk::kLmThreads, fsmem, st>>>(qi, N, o, map.row_mul, rows, list, count, counters);
+        ctx->launches++;
+        DFK_CUDA(cudaGetLastError());
+    }
     return DFK_OK;
 }
 

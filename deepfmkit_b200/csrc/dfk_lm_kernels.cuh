@@ -126,6 +126,50 @@ DFK_D void ne_load(const double* s, NormalEq& n, int stride) {
     n.g1 = s[8 * stride]; n.g2 = s[9 * stride]; n.g3 = s[10 * stride]; n.ssq = s[11 * stride];
 }
 
+// One trip of the per-lane state machine: returns true when the fit has ended (p, ssq, steps final).
+struct FlatState {
+    double p[4];
+    double ssq;
+    int lam;  // -1: evaluate the starting point; 0..7: position in the damping ladder
+    int steps;
+};
+
+DFK_D bool flat_step(int N, const double* q, double* bes, double* nes, const LmOpts& o, FlatState& st, LmCounts& cnt) {
+    double dp[4] = {0.0, 0.0, 0.0, 0.0};
+    bool skip = false;
+    if (st.lam >= 0) {
+        NormalEq ne;
+        ne_load(nes, ne, kLmThreads);
+        damped_solve(ne, lambda_of(st.lam), dp);
+        cnt.n_solve++;
+        skip = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]) < 1e-15;  // fit.py:230
+    }
+    const double pt[4] = {st.p[0] + dp[0], st.p[1] + dp[1], st.p[2] + dp[2], st.p[3] + dp[3]};
+    NormalEq nt;
+    cnt.n_bessel_steps += skip ? 0 : bessel_j_upto(pt[1], N + 1, bes, kLmThreads);
+    eval_state<1>(N, q, 1, bes, kLmThreads, pt, nt);
+    if (st.lam < 0) {
+        cnt.n_state++;
+        ne_store(nes, nt, kLmThreads);
+        st.ssq = nt.ssq;
+        st.lam = 0;
+        return o.max_steps <= 0;
+    }
+    if (!skip) cnt.n_ssq++;
+    if (!skip && nt.ssq < st.ssq) {  // first strictly better damping wins (fit.py:240-243)
+        const double moved = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]);
+        st.p[0] = pt[0]; st.p[1] = pt[1]; st.p[2] = pt[2]; st.p[3] = pt[3];
+        ne_store(nes, nt, kLmThreads);
+        st.ssq = nt.ssq;
+        cnt.n_state++;
+        ++st.steps;
+        st.lam = 0;
+        // fit.py:255 compares the accepted ssq with its own recomputation: 0 < conv_improve unless it is <= 0
+        return ((0.0 < o.conv_improve) && moved < o.conv_param) || st.steps >= o.max_steps;
+    }
+    return ++st.lam == 8;  // no damping improved (fit.py:246)
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double* __restrict__ qi, long long nfit, FitMap map,
                                                                    int N, GuessSrc guess, const double* __restrict__ dc,
@@ -138,14 +182,11 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double*
     const long long stride = static_cast<long long>(gridDim.x) * kLmThreads;
     long long f = static_cast<long long>(blockIdx.x) * kLmThreads + threadIdx.x;
     LmCounts cnt = {};
-    double p[4] = {0.0, 0.0, 0.0, 0.0};
-    double ssq = 0.0;
+    FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0};
     const double* q = qi;
     long long u = 0;
-    int lam = -1;  // -1: evaluate the starting point; 0..7: position in the damping ladder
-    int steps = 0;
     bool active = false;
-    // fetch the first fit this lane has to do (skipping units that are already fitted)
+    // fetch the next fit this lane has to do (skipping units that are already fitted)
     auto fetch = [&]() {
         active = false;
         while (f < nfit) {
@@ -159,63 +200,74 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double*
         q = qi + u * 2 * N;
         if (guess.ptr) {
             const double* g = guess.ptr + (guess.div == 1 ? u : u / guess.div) * guess.stride;
-            p[0] = g[0]; p[1] = g[1]; p[2] = g[2]; p[3] = g[3];
+            st.p[0] = g[0]; st.p[1] = g[1]; st.p[2] = g[2]; st.p[3] = g[3];
         } else {
-            p[0] = guess.val[0]; p[1] = guess.val[1]; p[2] = guess.val[2]; p[3] = guess.val[3];
+            st.p[0] = guess.val[0]; st.p[1] = guess.val[1]; st.p[2] = guess.val[2]; st.p[3] = guess.val[3];
         }
-        lam = -1;
-        steps = 0;
+        st.lam = -1;
+        st.steps = 0;
     };
     fetch();
     while (active) {
-        double dp[4] = {0.0, 0.0, 0.0, 0.0};
-        bool skip = false;
-        if (lam >= 0) {
-            NormalEq ne;
-            ne_load(nes, ne, kLmThreads);
-            damped_solve(ne, lambda_of(lam), dp);
-            cnt.n_solve++;
-            skip = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]) < 1e-15;  // fit.py:230
-        }
-        const double pt[4] = {p[0] + dp[0], p[1] + dp[1], p[2] + dp[2], p[3] + dp[3]};
-        NormalEq nt;
-        cnt.n_bessel_steps += skip ? 0 : bessel_j_upto(pt[1], N + 1, bes, kLmThreads);
-        eval_state<1>(N, q, 1, bes, kLmThreads, pt, nt);
-        bool finished = false;
-        if (lam < 0) {
-            cnt.n_state++;
-            ne_store(nes, nt, kLmThreads);
-            ssq = nt.ssq;
-            lam = 0;
-            finished = o.max_steps <= 0;
-        } else {
-            if (!skip) cnt.n_ssq++;
-            if (!skip && nt.ssq < ssq) {  // first strictly better damping wins (fit.py:240-243)
-                const double moved = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]);
-                p[0] = pt[0]; p[1] = pt[1]; p[2] = pt[2]; p[3] = pt[3];
-                ne_store(nes, nt, kLmThreads);
-                ssq = nt.ssq;
-                cnt.n_state++;
-                ++steps;
-                // fit.py:255 compares the accepted ssq with its own recomputation: 0 < conv_improve unless it is <= 0
-                finished = ((0.0 < o.conv_improve) && moved < o.conv_param) || steps >= o.max_steps;
-                lam = 0;
-            } else if (++lam == 8) {
-                finished = true;  // no damping improved (fit.py:246)
-            }
-        }
-        if (finished) {
+        if (flat_step(N, q, bes, nes, o, st, cnt)) {
             double* row = rows + u * map.row_mul * kRowStride;
-            const bool done = ssq < o.fitok_threshold;
-            if (done) normalise_params(p);
-            row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
+            const bool done = st.ssq < o.fitok_threshold;
+            if (done) normalise_params(st.p);
+            row[0] = st.p[0]; row[1] = st.p[1]; row[2] = st.p[2]; row[3] = st.p[3];
             row[4] = dc ? dc[u] : 0.0;
-            row[5] = ssq;
+            row[5] = st.ssq;
             row[6] = done ? 0.0 : -1.0;
-            row[7] = static_cast<double>(steps);
+            row[7] = static_cast<double>(st.steps);
             if (!done) retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
             fetch();
         }
+    }
+    flush_counts(cnt, counts, true);
+}
+
+// Retry stage for MANY parked fits (a sweep cold-started far from the truth parks most of them): one thread per
+// fit.  The warp-per-fit retry kernel below spends 32 lanes on one fit -- right for a handful of stragglers, but
+// every lane then repeats the same Miller recurrence, so its cost per fit is that of 32 independent fits.  Here the
+// 51-point grid search runs in lock step (the same work for every lane) and the second descent through the per-lane
+// state machine; the two kernels split the work by the number of parked fits (kFlatRetryMin).
+constexpr int kFlatRetryMin = 4096;
+
+__global__ void __launch_bounds__(kLmThreads) lm_retry_flat_kernel(const double* __restrict__ qi, int N, LmOpts o,
+                                                                   long long row_mul, double* __restrict__ rows,
+                                                                   const int* __restrict__ retry_list,
+                                                                   const int* __restrict__ retry_count,
+                                                                   LmCounts* __restrict__ counts) {
+    extern __shared__ double lm_smem[];
+    double* bes = lm_smem + threadIdx.x;
+    double* nes = lm_smem + (N + 2) * kLmThreads + threadIdx.x;
+    const int n = *retry_count;
+    if (n < kFlatRetryMin) return;
+    LmCounts cnt = {};
+    for (long long i = static_cast<long long>(blockIdx.x) * kLmThreads + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * kLmThreads) {
+        const long long u = retry_list[i];
+        double* row = rows + u * row_mul * kRowStride;
+        const double* q = qi + u * 2 * N;
+        double p1[4] = {row[0], row[1], row[2], row[3]};
+        double ssq1 = row[5];
+        int steps1 = static_cast<int>(row[7]);
+        FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0};
+        grid_seed<1>(N, q, 1, bes, kLmThreads, o, st.p, cnt);
+        cnt.n_grid++;
+        if (st.p[0] != 0.0 || st.p[1] != 0.0 || st.p[2] != 0.0 || st.p[3] != 0.0) {  // np.any (NaN counts as true)
+            while (!flat_step(N, q, bes, nes, o, st, cnt)) {
+            }
+            if (st.ssq < ssq1) {  // fit.py:345-347: keep the second descent only if it is better
+                p1[0] = st.p[0]; p1[1] = st.p[1]; p1[2] = st.p[2]; p1[3] = st.p[3];
+                ssq1 = st.ssq;
+                steps1 = st.steps;
+            }
+        }
+        normalise_params(p1);
+        row[0] = p1[0]; row[1] = p1[1]; row[2] = p1[2]; row[3] = p1[3];
+        row[5] = ssq1;
+        row[6] = ssq1 < o.fitok_threshold ? 1.0 : 2.0;
+        row[7] = static_cast<double>(steps1);
     }
     flush_counts(cnt, counts, true);
 }
@@ -231,6 +283,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_retry_kernel(const double* __re
     const int lane = threadIdx.x & 31;
     const int warps_per_block = kLmThreads / 32;
     const int n = *retry_count;
+    if (n >= kFlatRetryMin) return;  // lm_retry_flat_kernel's share
     LmCounts cnt = {};
     for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
         const long long f = retry_list[i];

@@ -605,3 +605,35 @@ def test_bulk_parity_over_random_cold_starts(torch_mod):
     err = np.abs(rows[ok, :4] - ref[ok, :4])
     err[:, :2] /= np.abs(ref[ok, :2])
     assert err.max() <= PARAM_TOL, (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+def test_many_parked_fits_take_the_flat_retry_kernel(torch_mod):
+    """>= 4096 parked fits switch the retry stage from a warp per fit to a thread per fit.  The same 9000 cold fits
+    (init_m = 6, m_true in 9..21: nearly all need the grid fallback) in one call (thread per fit) and in chunks of
+    1500 (warp per fit) must agree, and a sample of them must agree with the oracle."""
+    from multiprocessing import Pool
+    from deepfmkit_b200 import nls_fit_batch
+    rng = np.random.RandomState(11)
+    n = 9000
+    ms = rng.uniform(9.0, 21.0, n)
+    phis = rng.uniform(-3, 3, n)
+    jobs = [(ms[i], 30.0, 5000 + i, 6.0, phis[i], 0.0) for i in range(n)]
+    sample = list(range(0, n, 45))
+    with Pool(min(16, os.cpu_count() or 1)) as pool:
+        res = pool.map(_bulk_case, [jobs[i] for i in sample], chunksize=10)
+    t = np.arange(400) / 200e3
+    x = np.stack([orc.snr_signal(ms[i], 200e3, 1000.0, 2e-3, 30.0, seed=5000 + i, phi0=phis[i]) for i in range(n)])
+    whole = nls_fit_batch(x, 200e3, 1000.0, 2, ndata=12, init_m=6.0, seeded=False)[:, 0, :]
+    assert np.mean(whole[:, 6] >= 1) > 0.9, "the sample must park most fits"
+    chunks = np.concatenate([nls_fit_batch(x[i:i + 1500], 200e3, 1000.0, 2, ndata=12, init_m=6.0, seeded=False)[:, 0, :]
+                             for i in range(0, n, 1500)])
+    assert np.array_equal(whole[:, 6], chunks[:, 6])
+    ok = whole[:, 6] < 2
+    assert np.max(np.abs(whole[ok, :4] - chunks[ok, :4])) < PARAM_TOL
+    ref = np.stack([r[1] for r in res])
+    got = whole[sample]
+    assert np.array_equal(got[:, 6], ref[:, 6])
+    okr = ref[:, 6] < 2
+    err = np.abs(got[okr, :4] - ref[okr, :4])
+    err[:, :2] /= np.abs(ref[okr, :2])
+    assert err.max() <= PARAM_TOL
