@@ -284,7 +284,7 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = _lib.Context(local)
+    ctx = _lib.Context(local, own_stream=True)
     stream = torch.cuda.Stream(device=local)
     w0 = 2.0 * np.pi * F_MOD / F_SAMP
     opts = tunables.current_lm_opts()

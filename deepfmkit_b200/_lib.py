@@ -129,11 +129,16 @@ def _host_array(a):
 class Context:
     """One dfk_ctx: a device, its streams and scratch. Not shared between threads."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, own_stream: bool = False):
+        """own_stream=False (default): device-pointer calls are issued on the legacy default stream, the one torch
+        uses unless told otherwise, so they are ordered with the torch kernels that produce their inputs.
+        own_stream=True: on the context's private non-blocking stream -- the caller orders things itself."""
         self.lib = load_library()
         self._h = _vp()
         _check(self.lib, self.lib.dfk_create(int(device), ctypes.byref(self._h)))
         self.device = int(device)
+        self._own_default = bool(own_stream)
+        self.use_default_stream()
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -165,6 +170,13 @@ class Context:
 
     def use_own_stream(self):
         _check(self.lib, self.lib.dfk_set_stream(self._h, None))
+
+    def use_default_stream(self):
+        """Back to the stream this context was created with (see __init__)."""
+        if self._own_default:
+            self.use_own_stream()
+        else:
+            _check(self.lib, self.lib.dfk_use_legacy_default_stream(self._h, 1))
 
     def synchronize(self):
         _check(self.lib, self.lib.dfk_synchronize(self._h))

@@ -175,7 +175,7 @@ def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_ps
             ctx.nls_fit_batch_dev(xt.data_ptr(), C, bpc, T, R, int(ndata), w0, init, init_dev_ptr, init_stride, seeded,
                                   fit_tunables.current_lm_opts(tunables_from), rows.data_ptr())
         finally:
-            ctx.use_own_stream()
+            ctx.use_default_stream()
         torch.cuda.current_stream(dev).synchronize()
     del keep
     return rows if return_tensor else rows.cpu().numpy()
@@ -218,6 +218,6 @@ def ekf_fit_batch(z, f_samp, f_mod, n, time_major=False, device=0, return_tensor
         try:
             ctx.ekf_dev(zt.data_ptr(), T, C, ld_t, ld_c, R, float(f_samp), float(f_mod), opts, rows.data_ptr())
         finally:
-            ctx.use_own_stream()
+            ctx.use_default_stream()
         torch.cuda.current_stream(dev).synchronize()
     return rows if return_tensor else rows.cpu().numpy()

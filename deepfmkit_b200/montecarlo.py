@@ -126,7 +126,7 @@ def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, 
                 done += nw
             torch.cuda.current_stream(dev).synchronize()
         finally:
-            ctx.use_own_stream()
+            ctx.use_default_stream()
     part = {"n": int(n_trials), "truth": truth.cpu().numpy(),
             "sum": torch.stack(stats["sum"]).sum(0).cpu().numpy(), "sumsq": torch.stack(stats["sumsq"]).sum(0).cpu().numpy(),
             "min": torch.stack(stats["min"]).min(0).values.cpu().numpy(),

@@ -98,7 +98,7 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
                 ctx.nls_fit_seeded_dev(xt.data_ptr(), nb, R, ndata, w0, seed, opts, rows.data_ptr())
             torch.cuda.current_stream(dev).synchronize()
         finally:
-            ctx.use_own_stream()
+            ctx.use_default_stream()
     return gather_rows(rows.cpu().numpy(), n_buffers_total, dst=0, group=group)
 
 

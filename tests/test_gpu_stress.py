@@ -1,0 +1,72 @@
+"""Randomised geometry sweep of the TMA-fed demodulation kernels against a plain numpy lock-in.
+
+The ring protocols of the fold / tile / single-period kernels (mbarrier phases, the issued-chunk counter, per-warp
+ownership of stages) fail as hangs or as stale data, and which warp meets which stage depends on the number of
+buffers, the ring depth and the group size -- so the sweep draws those at random (fixed seed) and repeats every
+launch, comparing with an independent CPU result.  compute-sanitizer is not available on this pool; this is the
+substitute.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def numpy_lockin(x, R, nh, w0):
+    nbuf = len(x) // R
+    t = np.arange(R)
+    k = np.arange(1, nh + 1)[:, None]
+    ang = (k * w0) * t[None, :]  # the reference's fl(fl(k*w0)*t)
+    xb = x[: nbuf * R].reshape(nbuf, R)
+    q = xb @ np.cos(ang).T / R
+    i = xb @ np.sin(ang).T / R
+    return np.concatenate([q, i], axis=1), xb.mean(axis=1)
+
+
+def test_random_geometries(monkeypatch):
+    import torch
+    from deepfmkit_b200 import _lib
+    ctx = _lib.Context(0)
+    ctx.use_torch_stream()  # the NaN pre-fills below are torch kernels: same stream, so they are ordered before ours
+    rng = np.random.RandomState(31337)
+    worst = 0.0
+    cases = 0
+    for trial in range(70):
+        kind = trial % 5
+        if kind == 0:    # single-period kernel: P % 4 == 0, n = 1
+            P, n = 4 * rng.randint(1, 65), 1
+        elif kind == 1:  # tile kernel, grouped buffers
+            P, n = 2 * rng.randint(1, 129), rng.randint(1, 5)
+        elif kind == 2:  # tile kernel, one buffer per group
+            P, n = 2 * rng.randint(20, 129), rng.randint(8, 40)
+        elif kind == 3:  # fold kernel
+            P, n = 2 * rng.randint(129, 1025), rng.randint(1, 9)
+        else:            # odd period folded over two periods
+            P, n = 2 * rng.randint(3, 300) + 1, 2 * rng.randint(1, 8)
+        nh = int(rng.randint(1, 21))
+        nbuf = int(rng.choice([1, 2, 7, 8, 9, 63, 148, 149, 300, 1185, 2371, 5000]))
+        if P * n * nbuf > 40_000_000:
+            nbuf = max(1, 40_000_000 // (P * n))
+        R = P * n
+        w0 = 2.0 * np.pi * 1000.0 / (1000.0 * P)
+        if rng.rand() < 0.3:
+            monkeypatch.setenv("DFK_TILE_NSTAGES", str(int(rng.randint(2, 6))))
+        else:
+            monkeypatch.delenv("DFK_TILE_NSTAGES", raising=False)
+        t = np.arange(nbuf * R)
+        x = 1.0 + np.cos(0.3 + 4.0 * np.cos(2 * np.pi * t / P + 0.1)) + 0.05 * rng.randn(nbuf * R)
+        ref_qi, ref_dc = numpy_lockin(x, R, nh, w0)
+        xd = torch.from_numpy(x).cuda()
+        scale = np.maximum(np.abs(ref_qi).max(axis=1, keepdims=True), 1e-3)
+        for rep in range(2):
+            qi = torch.full((nbuf, 2 * nh), float("nan"), dtype=torch.float64, device="cuda")
+            dc = torch.full((nbuf,), float("nan"), dtype=torch.float64, device="cuda")
+            ctx.demod(xd.data_ptr(), nbuf, R, nh, w0, qi.data_ptr(), dc.data_ptr())
+            ctx.synchronize()
+            err = float(np.max(np.abs(qi.cpu().numpy() - ref_qi) / scale))
+            assert err <= 1e-12, (trial, kind, P, n, nh, nbuf, rep, err)
+            assert np.max(np.abs(dc.cpu().numpy() - ref_dc)) <= 1e-13, (trial, kind, P, n, nh, nbuf, rep)
+            worst = max(worst, err)
+        cases += 1
+    ctx.close()
+    assert cases == 70 and worst <= 1e-12
