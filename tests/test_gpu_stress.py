@@ -70,3 +70,36 @@ def test_random_geometries(monkeypatch):
         cases += 1
     ctx.close()
     assert cases == 70 and worst <= 1e-12
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_entry_boundaries(pinned):
+    """Record lengths straddling the host pipeline's boundaries (64 MiB staging pieces, 128 MiB device slabs), from
+    pageable and from pinned memory: the rows must equal those of the device-resident call, bit for bit."""
+    import torch
+    from deepfmkit_b200 import _lib
+    ctx = _lib.Context(0)
+    R, nh = 1000, 6
+    w0 = 2.0 * np.pi / 100.0
+    stage, slab = (64 << 20) // (R * 8), (128 << 20) // (R * 8)
+    for nbuf in (1, stage - 1, stage, stage + 1, slab - 1, slab, slab + 1, 2 * slab + 3):
+        xd = torch.empty(nbuf * R + 7, dtype=torch.float64, device="cuda")  # + a ragged tail the entry must ignore
+        ctx.synth_snr_dev(xd.data_ptr(), nbuf * R + 7, 1, 100e3, 1000.0, 6.0, snr_db=40.0, seed=nbuf)
+        ref = torch.empty((nbuf, 8), dtype=torch.float64, device="cuda")
+        ctx.nls_fit_dev(xd.data_ptr(), nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0], True, None, ref.data_ptr())
+        ctx.synchronize()
+        if pinned:
+            xh = torch.empty(nbuf * R + 7, dtype=torch.float64, pin_memory=True)
+            xh.copy_(xd)
+            x = xh.numpy()
+        else:
+            x = xd.cpu().numpy()
+        rows = ctx.nls_fit_host(x, R, nh, w0, [1.6, 6.0, 0.0, 0.0], seeded=True)
+        assert rows.shape == (nbuf, 8)
+        r = ref.cpu().numpy()
+        # slabs are fitted separately, so the lanes-per-fit choice (hence the summation order) can differ from the
+        # one-launch device call: equality to rounding, not to the bit
+        assert np.array_equal(rows[:, 6], r[:, 6]), (nbuf, pinned)
+        assert np.max(np.abs(rows[:, :6] - r[:, :6])) < 1e-9, (nbuf, pinned, np.max(np.abs(rows[:, :6] - r[:, :6])))
+        assert np.array_equal(rows[:, 4], r[:, 4]), (nbuf, pinned)  # dc comes from the demodulation alone: bit equal
+    ctx.close()
