@@ -286,6 +286,9 @@ DFK_HD double lm_descend(int N, const double* qi, int qs, double* bes, int bs, c
                          int& accepted_steps, LmCounts& cnt) {
     NormalEq ne;
     cnt.n_bessel_steps += bessel_j_upto(p[1], N + 1, bes, bs);
+    // m the Bessel column currently holds: near convergence the steps of neighbouring dampings differ by less than
+    // an ulp of m, the trial m is then bit-identical and the column (a pure function of m) need not be rebuilt
+    double m_held = p[1];
     eval_state<G>(N, qi, qs, bes, bs, p, ne);
     cnt.n_state++;
     double ssq = ne.ssq;
@@ -301,7 +304,10 @@ DFK_HD double lm_descend(int N, const double* qi, int qs, double* bes, int bs, c
             const double nrm = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2] + dp[3] * dp[3]);
             if (nrm < 1e-15) continue;  // fit.py:230
             const double pt[4] = {p[0] + dp[0], p[1] + dp[1], p[2] + dp[2], p[3] + dp[3]};
-            cnt.n_bessel_steps += bessel_j_upto(pt[1], N + 1, bes, bs);
+            if (pt[1] != m_held) {
+                cnt.n_bessel_steps += bessel_j_upto(pt[1], N + 1, bes, bs);
+                m_held = pt[1];
+            }
             const double st = eval_ssq<G>(N, qi, qs, bes, bs, pt);
             cnt.n_ssq++;
             if (st < best_ssq) {  // first strictly better damping wins (fit.py:240-243)

@@ -132,6 +132,7 @@ struct FlatState {
     double ssq;
     int lam;  // -1: evaluate the starting point; 0..7: position in the damping ladder
     int steps;
+    double m_held;  // m the Bessel column currently holds (NaN: none): a bit-identical trial m reuses the column
 };
 
 DFK_D bool flat_step(int N, const double* q, double* bes, double* nes, const LmOpts& o, FlatState& st, LmCounts& cnt) {
@@ -146,7 +147,10 @@ DFK_D bool flat_step(int N, const double* q, double* bes, double* nes, const LmO
     }
     const double pt[4] = {st.p[0] + dp[0], st.p[1] + dp[1], st.p[2] + dp[2], st.p[3] + dp[3]};
     NormalEq nt;
-    cnt.n_bessel_steps += skip ? 0 : bessel_j_upto(pt[1], N + 1, bes, kLmThreads);
+    if (!skip && !(pt[1] == st.m_held)) {
+        cnt.n_bessel_steps += bessel_j_upto(pt[1], N + 1, bes, kLmThreads);
+        st.m_held = pt[1];
+    }
     eval_state<1>(N, q, 1, bes, kLmThreads, pt, nt);
     if (st.lam < 0) {
         cnt.n_state++;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double*
     const long long stride = static_cast<long long>(gridDim.x) * kLmThreads;
     long long f = static_cast<long long>(blockIdx.x) * kLmThreads + threadIdx.x;
     LmCounts cnt = {};
-    FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0};
+    FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0, 0.0};
     const double* q = qi;
     long long u = 0;
     bool active = false;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(kLmThreads, MINB) lm_flat_kernel(const double*
         }
         st.lam = -1;
         st.steps = 0;
+        st.m_held = __longlong_as_double(0x7ff8000000000000ll);  // NaN: column not built yet
     };
     fetch();
     while (active) {
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_retry_flat_kernel(const double*
         double p1[4] = {row[0], row[1], row[2], row[3]};
         double ssq1 = row[5];
         int steps1 = static_cast<int>(row[7]);
-        FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0};
+        FlatState st = {{0.0, 0.0, 0.0, 0.0}, 0.0, -1, 0, __longlong_as_double(0x7ff8000000000000ll)};
         grid_seed<1>(N, q, 1, bes, kLmThreads, o, st.p, cnt);
         cnt.n_grid++;
         if (st.p[0] != 0.0 || st.p[1] != 0.0 || st.p[2] != 0.0 || st.p[3] != 0.0) {  // np.any (NaN counts as true)
