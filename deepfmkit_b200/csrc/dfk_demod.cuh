@@ -4,18 +4,23 @@
 //   Q_k = mean(x[t] * cos(fl((k)*w0)*t)),  I_k = mean(x[t] * sin(fl(k*w0)*t)),  k = 1..N,  dc = mean(x),
 // with t restarting at 0 in every buffer.
 //
-// demod_fold_kernel -- the bandwidth-bound path.  Needs a whole even number P of samples per modulation
-//   period and whole periods per buffer (dfk_demod_plan.h).  A persistent CTA streams its buffers from HBM
-//   with 1-D TMA bulk copies (cp.async.bulk, one elected producer lane, mbarrier ring) and folds the
-//   periods onto one: S_j = sum_c x[j + cP] -- one DADD per 8 bytes (plus one DFMA for the drift sum).
-//   The N harmonics are then taken from the folded period with the j <-> P-j symmetry
-//   (cos(k th_j) even, sin(k th_j) odd) by a rotation recurrence per lane and a warp-shuffle reduction.
-//   Every sample is read from HBM exactly once: 8 B/sample + 8(2N+1) B/buffer written.
+// Four kernels, chosen by the launcher in dfk_b200.cu from the geometry (dfk_demod_plan.h):
 //
-// demod_direct_kernel -- any R and w0 (non-integer period): one CTA per buffer, harmonics in blocks of
-//   kDirectKB with a per-thread rotation recurrence re-synchronised with sincos every kDirectResync
-//   steps.  Compute-bound (6 fp64 ops per sample and harmonic); later harmonic blocks re-read the
-//   buffer from L1/L2.
+// demod_fold_kernel   -- long fold lengths (P > 256, e.g. 1 MHz / 1 kHz).  Needs a whole even number P of samples
+//   that holds whole modulation periods, and whole folds per buffer.  A persistent CTA streams its buffers from
+//   HBM with 1-D TMA bulk copies (cp.async.bulk, one elected producer lane, mbarrier ring) and folds the periods
+//   onto one: S_j = sum_c x[j + cP] -- one DADD per 8 bytes (plus one DFMA for the optional drift sum).  The N
+//   harmonics are then taken from the folded period with the j <-> P-j symmetry (cos(k th_j) even, sin(k th_j)
+//   odd) by a rotation recurrence per lane and a warp-shuffle reduction.
+// demod_tile_kernel   -- short fold lengths (P <= 256): no CTA-wide synchronisation, a warp owns its group of
+//   buffers from the TMA stage to the outputs, harmonics by a product with a twiddle table in shared memory.
+// demod_period_kernel -- one period per buffer (R = P, P % 4 == 0): the tile scheme with quarter-wave symmetry and
+//   a 2 x 4 register tile per lane, because at this shape the product, not HBM, is the bound.
+// demod_direct_kernel -- anything else (incommensurate period, unaligned pointer, strided channels): one CTA per
+//   buffer, harmonics in blocks of kDirectKB with a per-thread rotation recurrence re-synchronised with sincos
+//   every kDirectResync steps.  Compute-bound; later harmonic blocks re-read the buffer from L1/L2.
+//
+// In the three TMA kernels every sample is read from HBM exactly once: 8 B/sample + 8(2N+1) B/buffer written.
 #pragma once
 #include "dfk_common.cuh"
 #include "dfk_demod_plan.h"

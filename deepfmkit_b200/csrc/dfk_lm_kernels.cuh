@@ -3,9 +3,12 @@
 // Stage 1 (lm_first_kernel<G>): G lanes per fit run the first descent (fit.py:331).  A fit that ends
 //   below FITOK_THRESHOLD is finished: status 0, normalised, row written.  The others park their
 //   (p, ssq, steps) in the row and append their index to a retry list.
-// Stage 2 (lm_retry_kernel): one warp per parked fit runs the grid-search fallback (51 m candidates
-//   spread over the lanes) and the second descent (fit.py:336-349).  Splitting the stages keeps the
-//   20-40x more expensive fallback from stalling warps whose other fits converged at once.
+//   Cold batches (fits of a warp needing very different numbers of steps) use lm_flat_kernel instead: the same
+//   driver as a per-lane state machine with immediate refill.
+// Stage 2 (lm_retry_kernel / lm_retry_flat_kernel): the grid-search fallback (51 m candidates) and the second
+//   descent (fit.py:336-349) for the parked fits -- a warp per fit for a handful of stragglers, a thread per fit when
+//   thousands are parked.  Splitting the stages keeps the 20-40x more expensive fallback from stalling warps whose
+//   other fits converged at once.
 //
 // Bessel columns live in shared memory, one column per thread (index k * blockDim.x + threadIdx.x), so
 // the Miller recurrence -- evaluated redundantly by the lanes of a group -- never conflicts on banks.
