@@ -18,7 +18,7 @@ for name, f_samp, n, nd, C, secs, cold in (("cfg2", 1e6, 20, 10, 1, 3600.0, Fals
     out = {}
     for flat in ("0", "2"):
         for blocks in ("4",):
-            os.environ["DFK_LM_FLAT"] = flat; os.environ["DFK_LM_FLAT_BLOCKS"] = blocks
+            _lib.load_library().dfk_dev_set(b"DFK_LM_FLAT", int(flat)); _lib.load_library().dfk_dev_set(b"DFK_LM_FLAT_BLOCKS", int(blocks))
             rows = torch.zeros((nbuf, 8), dtype=torch.float64, device="cuda")
             opts = _lib.default_lm_opts(); opts.lanes_per_fit = 1
             ctx.lm_counters(reset=True)

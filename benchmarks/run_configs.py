@@ -110,8 +110,8 @@ def ekf_case(ctx, name, channels, seconds, reps, time_major, note="", start_s=0.
     if k0 > 0:  # a slab late in the record: start from a converged-looking state
         state[:, 0], state[:, 1], state[:, 4], state[:, 30] = 1.0, 6.0, 1.15, 1e-4
         state[:, 2] = torch.arange(channels, device="cuda") * (2 * np.pi / channels)
-        for i in range(5):
-            state[:, 5 + 6 * i] = 1e-6
+        for idx in (0, 5, 9, 12, 14):  # diagonal of the packed upper triangle
+            state[:, 5 + idx] = 1e-6
     keep = state.clone()
 
     def run():

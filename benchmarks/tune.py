@@ -53,12 +53,11 @@ def main():
         from deepfmkit_b200 import _lib as L
         stages = [int(v) for v in os.environ.get("TUNE_STAGES", "16384,24576,32768,40960,49152,65536").split(",")]
         for drift, ctas, nst, stage in itertools.product(("",), (1, 2, 3), (2, 3, 4, 5, 6, 7), stages):
-            os.environ["DFK_FOLD_DRIFT"] = drift
-            os.environ["DFK_FOLD_CTAS"] = str(ctas)
-            os.environ["DFK_FOLD_NSTAGES"] = str(nst)
-            os.environ["DFK_FOLD_STAGE_BYTES"] = str(stage)
-            if not drift:
-                del os.environ["DFK_FOLD_DRIFT"]
+            L.load_library().dfk_dev_clear()
+            for key, val in (("DFK_FOLD_CTAS", ctas), ("DFK_FOLD_NSTAGES", nst), ("DFK_FOLD_STAGE_BYTES", stage)):
+                L.load_library().dfk_dev_set(key.encode(), int(val))
+            if drift:
+                L.load_library().dfk_dev_set(b"DFK_FOLD_DRIFT", int(drift))
             qi.zero_()
             try:
                 t = timed(lambda: ctx.demod(x.data_ptr(), nbuf, R, nd, w0, qi.data_ptr(), dc.data_ptr()))
@@ -75,8 +74,9 @@ def main():
     else:
         ctx.demod(x.data_ptr(), nbuf, R, nd, w0, qi.data_ptr(), dc.data_ptr())
         guess = torch.tensor([1.0, 6.0, 0.0, 0.0], dtype=torch.float64, device="cuda")
+        from deepfmkit_b200 import _lib as L
         for minb, lanes in itertools.product((4, 6, 8), (1, 2, 4, 8)):
-            os.environ["DFK_LM_MINB"] = str(minb)
+            L.load_library().dfk_dev_set(b"DFK_LM_MINB", int(minb))
             opts = _lib.default_lm_opts()
             opts.lanes_per_fit = lanes
             t = timed(lambda: ctx.lm_fit(qi.data_ptr(), nbuf, nd, guess.data_ptr(), 0, dc.data_ptr(), opts, rows.data_ptr()))

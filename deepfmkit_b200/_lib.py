@@ -16,6 +16,10 @@ from ._build import LIB_PATH
 
 ROW_STRIDE = 8
 MAX_HARMONICS = 64
+ABI_VERSION = 2
+PROFILE_KINDS = 4
+SCHED_INDEPENDENT = 0   # every buffer a cold start from init
+SCHED_EACH = -1         # every buffer its own chunk, seeded from buffer 0 (pool schedule at n_cores >= nbuf - 1)
 ROW_COLUMNS = ("amp", "m", "phi", "psi", "dc", "ssq", "fitok")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -31,7 +35,7 @@ class LmOpts(ctypes.Structure):
 
 class EkfOpts(ctypes.Structure):
     _fields_ = [("init", ctypes.c_double * 4), ("p0_diag", ctypes.c_double * 5),
-                ("q_diag", ctypes.c_double * 5), ("r_val", ctypes.c_double)]
+                ("q_diag", ctypes.c_double * 5), ("r_val", ctypes.c_double), ("init_dc", ctypes.c_double)]
 
 
 class LmCounters(ctypes.Structure):
@@ -58,7 +62,7 @@ SYMBOLS = {
     "dfk_demod": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
     "dfk_lm_fit": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
-    "dfk_nls_fit_seeded_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_nls_fit_seeded_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_batch_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
                                              ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
@@ -68,11 +72,15 @@ SYMBOLS = {
                                               ctypes.c_uint64]),
     "dfk_synth_snr_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d, ctypes.c_uint64]),
     "dfk_nls_fit_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
+    "dfk_nls_fit_seeded_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
+    "dfk_set_host_slab_bytes": (ctypes.c_int, [_vp, _i64]),
     "dfk_lm_counters_read": (ctypes.c_int, [_vp, ctypes.POINTER(LmCounters), _i32]),
     "dfk_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "dfk_profile_read": (ctypes.c_int, [_vp, c_double_p, ctypes.POINTER(_i64), _i32]),
     "dfk_probe_fp64": (ctypes.c_int, [_vp, c_double_p]),
+    "dfk_dev_set": (ctypes.c_int, [ctypes.c_char_p, _i32]),
+    "dfk_dev_clear": (None, []),
     "dfk_launch_count": (_i64, [_vp]),
     "dfk_demod_path": (ctypes.c_int, [_i64, _d]),
     "dfk_bessel_dev": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
@@ -98,10 +106,23 @@ def load_library():
             fn = getattr(lib, name)
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.dfk_abi_version() != 1:
+        if lib.dfk_abi_version() != ABI_VERSION:
             raise RuntimeError("libdfk_b200.so ABI version mismatch")
         _lib = lib
         return lib
+
+
+def schedule_code(seeded) -> int:
+    """The C ABI's `seeded` argument: False/0 -> independent starts, True -> every buffer seeded from buffer 0
+    (DFK_SCHED_EACH), an int k >= 1 -> the reference's k-chunk chain schedule (k = 1: the sequential chain)."""
+    if seeded is True:
+        return SCHED_EACH
+    if seeded is False or seeded is None:
+        return SCHED_INDEPENDENT
+    k = int(seeded)
+    if k < -1:
+        raise ValueError("schedule must be False, True, -1 or a chunk count >= 1")
+    return k
 
 
 def _check(lib, rc):
@@ -191,19 +212,19 @@ class Context:
 
     def nls_fit_dev(self, x_ptr, nbuf, R, N, w0, init, seeded, opts, rows_ptr):
         init_arr = (ctypes.c_double * 4)(*[float(v) for v in init])
-        _check(self.lib, self.lib.dfk_nls_fit_dev(self._h, x_ptr, nbuf, R, N, w0, init_arr, int(bool(seeded)),
+        _check(self.lib, self.lib.dfk_nls_fit_dev(self._h, x_ptr, nbuf, R, N, w0, init_arr, schedule_code(seeded),
                                                   ctypes.byref(opts) if opts is not None else None, rows_ptr))
 
-    def nls_fit_seeded_dev(self, x_ptr, nbuf, R, N, w0, seed, opts, rows_ptr):
+    def nls_fit_seeded_dev(self, x_ptr, nbuf, R, N, w0, seed, opts, rows_ptr, chunks=1):
         seed_arr = (ctypes.c_double * 4)(*[float(v) for v in seed])
-        _check(self.lib, self.lib.dfk_nls_fit_seeded_dev(self._h, x_ptr, nbuf, R, N, w0, seed_arr,
+        _check(self.lib, self.lib.dfk_nls_fit_seeded_dev(self._h, x_ptr, nbuf, R, N, w0, seed_arr, int(chunks),
                                                          ctypes.byref(opts) if opts is not None else None, rows_ptr))
 
     def nls_fit_batch_dev(self, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init, init_dev_ptr, init_stride, seeded,
                           opts, rows_ptr):
         init_arr = (ctypes.c_double * 4)(*[float(v) for v in init]) if init is not None else None
         _check(self.lib, self.lib.dfk_nls_fit_batch_dev(self._h, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init_arr,
-                                                        init_dev_ptr, init_stride, int(bool(seeded)),
+                                                        init_dev_ptr, init_stride, schedule_code(seeded),
                                                         ctypes.byref(opts) if opts is not None else None, rows_ptr))
 
     def ekf_dev(self, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, rows_ptr):
@@ -230,14 +251,26 @@ class Context:
 
     # ---- host-pointer calls ----------------------------------------------------------------------------
     def nls_fit_host(self, x, R, N, w0, init, seeded=True, opts=None, rows_out=None):
-        """x: 1-D float64 host array (numpy or a pinned torch tensor's numpy view). Returns rows[nbuf, 8]."""
+        """x: 1-D float64 host array (numpy or a pinned torch tensor's numpy view). Returns rows[nbuf, 8].
+        seeded: see schedule_code (True: every buffer from buffer 0's result; k: the reference's k-chunk chain)."""
         x, xp = _host_array(x)
         nbuf = x.size // int(R)
         rows = rows_out if rows_out is not None else np.empty((nbuf, ROW_STRIDE), dtype=np.float64)
         init_arr = (ctypes.c_double * 4)(*[float(v) for v in init])
         _check(self.lib, self.lib.dfk_nls_fit_host(self._h, xp, x.size, int(R), int(N), float(w0), init_arr,
-                                                   int(bool(seeded)), ctypes.byref(opts) if opts is not None else None,
+                                                   schedule_code(seeded), ctypes.byref(opts) if opts is not None else None,
                                                    rows.ctypes.data))
+        return rows
+
+    def nls_fit_seeded_host(self, x, R, N, w0, seed, chunks=1, opts=None, rows_out=None):
+        """A host slab of a record whose buffer 0 was fitted elsewhere: `chunks` chains started from seed[4]."""
+        x, xp = _host_array(x)
+        nbuf = x.size // int(R)
+        rows = rows_out if rows_out is not None else np.empty((nbuf, ROW_STRIDE), dtype=np.float64)
+        seed_arr = (ctypes.c_double * 4)(*[float(v) for v in seed])
+        _check(self.lib, self.lib.dfk_nls_fit_seeded_host(self._h, xp, x.size, int(R), int(N), float(w0), seed_arr,
+                                                          int(chunks), ctypes.byref(opts) if opts is not None else None,
+                                                          rows.ctypes.data))
         return rows
 
     def ekf_host(self, z, R, f_samp, f_mod, opts=None):
@@ -250,6 +283,10 @@ class Context:
                                                ctypes.byref(opts) if opts is not None else None, rows.ctypes.data))
         return rows
 
+    def set_host_slab_bytes(self, nbytes=0):
+        """Slab size of the host-pointer entries (0: defaults); small values make a short record stream."""
+        _check(self.lib, self.lib.dfk_set_host_slab_bytes(self._h, int(nbytes)))
+
     # ---- introspection ---------------------------------------------------------------------------------
     def lm_counters(self, reset=False) -> dict:
         c = LmCounters()
@@ -261,11 +298,11 @@ class Context:
 
     def profile_read(self, reset=False) -> dict:
         """Summed device milliseconds and region counts: demod launches and LM launches."""
-        ms = (ctypes.c_double * 3)()
-        n = (_i64 * 3)()
+        ms = (ctypes.c_double * PROFILE_KINDS)()
+        n = (_i64 * PROFILE_KINDS)()
         _check(self.lib, self.lib.dfk_profile_read(self._h, ms, n, int(bool(reset))))
         return {"demod_ms": ms[0], "demod_regions": int(n[0]), "lm_ms": ms[1], "lm_regions": int(n[1]),
-                "seed_ms": ms[2], "seed_regions": int(n[2])}
+                "seed_ms": ms[2], "seed_regions": int(n[2]), "ekf_ms": ms[3], "ekf_regions": int(n[3])}
 
     def probe_fp64_tflops(self) -> float:
         v = ctypes.c_double()
@@ -274,6 +311,23 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.dfk_launch_count(self._h))
+
+
+class dev_overrides:
+    """``with dev_overrides(DFK_NO_TILE=1): ...`` -- kernel-selection overrides for tuning runs and A/B tests,
+    set through the library's explicit call (it never reads the environment) and cleared on exit."""
+
+    def __init__(self, **values):
+        self.values = values
+
+    def __enter__(self):
+        lib = load_library()
+        for k, v in self.values.items():
+            _check(lib, lib.dfk_dev_set(k.encode(), int(v)))
+        return self
+
+    def __exit__(self, *exc):
+        load_library().dfk_dev_clear()
 
 
 def demod_path(R, w0) -> int:

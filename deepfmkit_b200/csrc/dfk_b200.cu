@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -62,14 +64,16 @@ struct dfk_ctx {
     cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
     DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc, qi_seed, dc_seed;
     int64_t launches = 0;
+    bool stats_ready = false;      // ctx->stats already holds whole-record moments (streamed EKF)
+    size_t host_slab_bytes = 0;    // 0 = defaults; else the slab size of the host-pointer entries (tests force streaming)
     // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the
-    // demod launch [0] and around the LM launches [1], summed on read
+    // demod launch [0], the LM launches [1], the side-stream seed fits [2] and the EKF kernel [3], summed on read
     bool profiling = false;
     static constexpr int kProfSlots = 512;
-    cudaEvent_t prof_ev[3][kProfSlots][2] = {};
-    int prof_used[3] = {0, 0, 0};
-    double prof_ms[3] = {0.0, 0.0, 0.0};
-    int64_t prof_n[3] = {0, 0, 0};
+    cudaEvent_t prof_ev[DFK_PROFILE_KINDS][kProfSlots][2] = {};
+    int prof_used[DFK_PROFILE_KINDS] = {};
+    double prof_ms[DFK_PROFILE_KINDS] = {};
+    int64_t prof_n[DFK_PROFILE_KINDS] = {};
     cudaStream_t stream() const { return use_user ? user_stream : own_stream; }
 };
 
@@ -96,7 +100,7 @@ int ensure(dfk_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 int prof_drain(dfk_ctx* ctx) {  // fold recorded event pairs into the totals (synchronises)
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < DFK_PROFILE_KINDS; ++k) {
         for (int i = 0; i < ctx->prof_used[k]; ++i) {
             DFK_CUDA(cudaEventSynchronize(ctx->prof_ev[k][i][1]));
             float ms = 0.f;
@@ -143,14 +147,42 @@ struct Guard {  // make the context's device current for the duration of a call
     }
 };
 
+// Host-pointer entries enqueue DMA from caller memory and from the pinned stagers on three streams.  If such a call
+// leaves early on an error, everything already queued must drain before the caller may free or reuse its record.
+struct HostCallGuard {
+    dfk_ctx* ctx;
+    bool finished = false;
+    explicit HostCallGuard(dfk_ctx* c) : ctx(c) {}
+    void done() { finished = true; }
+    ~HostCallGuard() {
+        if (finished) return;
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamSynchronize(ctx->stream());
+    }
+};
+
 #define DFK_ENTER(ctx)                                             \
     if (!(ctx)) return fail(DFK_ERR_ARG, "null context");          \
     Guard guard_(ctx);                                             \
     if (!guard_.ok) return fail(DFK_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
 
-int env_int(const char* name, int fallback) {
-    const char* v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : fallback;
+// Development overrides of kernel choice and geometry (benchmarks/tune.py, the kernel A/B tests).  They are set
+// by an explicit call, dfk_dev_set("DFK_NO_TILE", 1); the library never reads the environment, so nothing outside
+// the calling program can change which kernel runs.
+struct DevOverride {
+    char name[32];
+    int value;
+};
+DevOverride g_dev[16];
+std::atomic<int> g_dev_count{0};
+std::mutex g_dev_mutex;
+
+int dev_int(const char* name, int fallback) {
+    const int n = g_dev_count.load(std::memory_order_acquire);
+    for (int i = 0; i < n; ++i)
+        if (std::strcmp(g_dev[i].name, name) == 0) return g_dev[i].value;
+    return fallback;
 }
 
 dfk::LmOpts to_opts(const dfk_lm_opts* o) {
@@ -190,8 +222,8 @@ struct FoldGeometry {
 bool fold_geometry(const dfk_ctx* ctx, const dfk::DemodPlan& pl, int N, bool leave_room, FoldGeometry* g) {
     const int P = static_cast<int>(pl.P);
     // development overrides (tuning runs only): DFK_FOLD_STAGE_BYTES, DFK_FOLD_NSTAGES, DFK_FOLD_CTAS
-    const int env_stage = env_int("DFK_FOLD_STAGE_BYTES", 0), env_nst = env_int("DFK_FOLD_NSTAGES", 0),
-              env_ctas = env_int("DFK_FOLD_CTAS", 0);
+    const int env_stage = dev_int("DFK_FOLD_STAGE_BYTES", 0), env_nst = dev_int("DFK_FOLD_NSTAGES", 0),
+              env_ctas = dev_int("DFK_FOLD_CTAS", 0);
     int pps = (env_stage > 0 ? env_stage : dfk::kFoldStageBytes) / (P * 8);
     if (pps < 1) pps = 1;
     if (pps > pl.periods) pps = static_cast<int>(pl.periods);
@@ -265,7 +297,7 @@ int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid,
 // One period per buffer (R == P <= 256, P % 4 == 0, no drift term): the quarter-wave kernel.  1 = launched, 0 = does not fit.
 int try_launch_period(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int32_t N, double* qi,
                       double* dc, bool leave_room, cudaStream_t st) {
-    if (pl.periods != 1 || pl.kmul != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || env_int("DFK_NO_PERIOD", 0))
+    if (pl.periods != 1 || pl.kmul != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || dev_int("DFK_NO_PERIOD", 0))
         return 0;
     const int P = static_cast<int>(pl.P);
     int nst = 12;
@@ -295,16 +327,16 @@ int try_launch_period(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, i
 // 0 if the geometry does not fit it, < 0 on error.
 int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int64_t R, int32_t N,
                     double* qi, double* dc, bool leave_room, cudaStream_t st) {
-    if (pl.P > dfk::kTileMaxPeriod || env_int("DFK_NO_TILE", 0)) return 0;
+    if (pl.P > dfk::kTileMaxPeriod || dev_int("DFK_NO_TILE", 0)) return 0;
     const int P = static_cast<int>(pl.P), n = static_cast<int>(pl.periods);
     int nbw = 8;
     while (nbw > 1 && static_cast<int64_t>(nbw) * R * 8 > dfk::kTileStageBytes) nbw >>= 1;
-    const int env_nbw = env_int("DFK_TILE_NBW", 0);  // development override
+    const int env_nbw = dev_int("DFK_TILE_NBW", 0);  // development override
     if (env_nbw == 1 || env_nbw == 2 || env_nbw == 4 || env_nbw == 8) nbw = env_nbw;
     int pps = dfk::kTileStageBytes / (P * 8);
     if (pps < 1) pps = 1;
     if (pps > nbw * n) pps = nbw * n;
-    int nst = env_int("DFK_TILE_NSTAGES", 12);
+    int nst = dev_int("DFK_TILE_NSTAGES", 12);
     size_t smem = 0;
     for (; nst >= 2; --nst) {
         smem = dfk::tile_smem_layout(P, N, nbw, pps, nst, pl.drift).total;
@@ -352,7 +384,7 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
                  double* qi, double* dc, cudaStream_t st, bool leave_room = false) {
     if (nbuf == 0) return DFK_OK;
     dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
-    const int env_drift = env_int("DFK_FOLD_DRIFT", -1);  // development override
+    const int env_drift = dev_int("DFK_FOLD_DRIFT", -1);  // development override
     if (env_drift >= 0) pl.drift = env_drift != 0;
     FoldGeometry g;
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (ld_c % 2) == 0;
@@ -423,7 +455,8 @@ int pick_lanes(const dfk_ctx* ctx, int64_t nfit, int N, int requested) {
 
 template <int G, int MINB, int TPB>
 int launch_first_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
-                   const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+                   const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st,
+                   int* flags) {
     const size_t smem = static_cast<size_t>(N + 2) * TPB * sizeof(double);
     DFK_CUDA(cudaFuncSetAttribute(dfk::lm_first_kernel<G, MINB, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
@@ -436,7 +469,7 @@ int launch_first_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map
     const int64_t fits_per_block = TPB / G;
     const int64_t blocks = (nfit + fits_per_block - 1) / fits_per_block;
     const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * 16));
-    dfk::lm_first_kernel<G, MINB, TPB><<<grid, TPB, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
+    dfk::lm_first_kernel<G, MINB, TPB><<<grid, TPB, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters, flags);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
@@ -448,7 +481,7 @@ int launch_flat(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, i
     DFK_CUDA(cudaFuncSetAttribute(dfk::lm_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     const int64_t blocks = (nfit + dfk::kLmThreads - 1) / dfk::kLmThreads;
-    const int per_sm = env_int("DFK_LM_FLAT_BLOCKS", 4);
+    const int per_sm = dev_int("DFK_LM_FLAT_BLOCKS", 4);
     const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * per_sm));
     dfk::lm_flat_kernel<4><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
     ctx->launches++;
@@ -458,16 +491,17 @@ int launch_flat(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, i
 
 template <int G>
 int launch_first(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
-                 const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+                 const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st,
+                 int* flags) {
     // 128 registers give 4 resident blocks per SM; the 96-register build (5 per SM, a few spills) is ~10 % slower
     // per fit but wins when it saves a whole wave of a small batch (cfg 2: 1407 blocks = 3 waves of 592 or 2 of 740)
     const int64_t blocks = (nfit + (dfk::kLmThreads / G) - 1) / (dfk::kLmThreads / G);
     const int64_t w4 = (blocks + 4 * ctx->sm_count - 1) / (4 * ctx->sm_count);
     const int64_t w5 = (blocks + 5 * ctx->sm_count - 1) / (5 * ctx->sm_count);
-    const int minb = env_int("DFK_LM_MINB", (w5 < w4 && w5 <= 3) ? 5 : 4);
+    const int minb = dev_int("DFK_LM_MINB", (w5 < w4 && w5 <= 3) ? 5 : 4);
     switch (minb) {
-        case 5: return launch_first_b<G, 5, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
-        default: return launch_first_b<G, 4, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 5: return launch_first_b<G, 5, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags);
+        default: return launch_first_b<G, 4, dfk::kLmThreads>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags);
     }
 }
 
@@ -485,7 +519,8 @@ int ensure_counters(dfk_ctx* ctx) {
 // numbers of steps -- measured, the per-lane state machine (lm_flat_kernel) is 1.56x faster than the lock-step
 // kernel on 4e6 cold N = 15 fits, but 0.84x on warm ones, hence the switch.
 int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs,
-              const double* dc, const dfk_lm_opts* opts, double* rows, cudaStream_t st, bool cold = false) {
+              const double* dc, const dfk_lm_opts* opts, double* rows, cudaStream_t st, bool cold = false,
+              const dfk::ChainPlan* chain = nullptr) {
     if (nfit == 0) return DFK_OK;
     const int64_t max_unit = (nfit - 1) * map.step + map.offset + 1;
     if (max_unit > std::numeric_limits<int>::max()) return fail(DFK_ERR_ARG, "more than 2^31-1 fit units in one call");
@@ -496,31 +531,49 @@ int launch_lm(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int
     if (rc) return rc;
     int* count = static_cast<int*>(ctx->retry.ptr);
     int* list = count + 4;
+    int* flags = nullptr;
+    if (chain) {  // the chain schedule marks parked units in place of the retry list (units the launch skips stay 0)
+        flags = list;
+        DFK_CUDA(cudaMemsetAsync(flags, 0, static_cast<size_t>(nfit) * sizeof(int), st));
+    }
     auto* counters = static_cast<dfk::LmCounts*>(ctx->counters.ptr);
     DFK_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
     const int requested = opts ? opts->lanes_per_fit : 0;
     const int G = pick_lanes(ctx, nfit, N, requested);
     if (requested == 0 && nfit <= 2 * static_cast<int64_t>(ctx->sm_count)) {
         // a handful of fits: one warp per fit in one-warp blocks, spread over all SMs
-        rc = launch_first_b<32, 4, 32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
-    } else if (G == 1 && (cold ? env_int("DFK_LM_FLAT", 1) != 0 : env_int("DFK_LM_FLAT", 0) == 2)) {
+        rc = launch_first_b<32, 4, 32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags);
+    } else if (G == 1 && !chain && (cold ? dev_int("DFK_LM_FLAT", 1) != 0 : dev_int("DFK_LM_FLAT", 0) == 2)) {
         rc = launch_flat(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
     } else
     switch (G) {
-        case 1: rc = launch_first<1>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
-        case 2: rc = launch_first<2>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
-        case 4: rc = launch_first<4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
-        case 8: rc = launch_first<8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
-        case 16: rc = launch_first<16>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
-        default: rc = launch_first<32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st); break;
+        case 1: rc = launch_first<1>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
+        case 2: rc = launch_first<2>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
+        case 4: rc = launch_first<4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
+        case 8: rc = launch_first<8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
+        case 16: rc = launch_first<16>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
+        default: rc = launch_first<32>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st, flags); break;
     }
     if (rc) return rc;
     const size_t smem = static_cast<size_t>(N + 2) * dfk::kLmThreads * sizeof(double);
+    const int64_t warps = dfk::kLmThreads / 32;
+    if (chain) {
+        if (map.step != 1 || map.offset != 0 || map.row_mul != 1) return fail(DFK_ERR_ARG, "chain schedule needs contiguous units");
+        DFK_CUDA(cudaFuncSetAttribute(dfk::lm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        DFK_CUDA(cudaFuncSetAttribute(dfk::lm_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        const int64_t spans = (nfit + 31) / 32;  // a warp scans 32 units at a time
+        const int grid = static_cast<int>(std::min<int64_t>((spans + warps - 1) / warps, static_cast<int64_t>(ctx->sm_count) * 8));
+        dfk::lm_chain_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, N, o, *chain, rows, flags, counters);
+        ctx->launches++;
+        DFK_CUDA(cudaGetLastError());
+        return DFK_OK;
+    }
     DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     DFK_CUDA(cudaFuncSetAttribute(dfk::lm_retry_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    const int64_t warps = dfk::kLmThreads / 32;
     const int grid = static_cast<int>(std::min<int64_t>((nfit + warps - 1) / warps, static_cast<int64_t>(ctx->sm_count) * 8));
     dfk::lm_retry_kernel<<<grid, dfk::kLmThreads, smem, st>>>(qi, N, o, map.row_mul, rows, list, count, counters);
     ctx->launches++;
@@ -616,16 +669,34 @@ dfk::GuessSrc guess_rows(const double* ptr, int64_t stride, int64_t div, bool sk
     return g;
 }
 
+// How the warm starts of a record are scheduled (fitters.py:370-428).
+struct Schedule {
+    int64_t chunks = -1;         // 0: every buffer an independent start from init (workers.py:167-173);
+                                 // k >= 1: buffer 0 cold, the rest in k chained chunks (k = 1: the sequential chain);
+                                 // -1: every buffer its own chunk (the pool schedule at n_cores >= nbuf - 1)
+    int64_t b0 = 0;              // buffers of the record that earlier calls have done (host slabs)
+    int64_t record_buffers = 0;  // buffers of the whole record (0: the launch is the record)
+    bool external_seed = false;  // init is the result of a buffer 0 that lives elsewhere (another GPU's slab)
+};
+
+dfk::ChainPlan chain_plan(const Schedule& sc, int64_t bpc) {
+    dfk::ChainPlan c;
+    c.bpc = bpc;
+    c.b0 = sc.b0;
+    c.first = sc.external_seed ? 0 : 1;
+    const int64_t M = std::max<int64_t>((sc.record_buffers ? sc.record_buffers : bpc) - c.first, 0);
+    const int64_t k = std::max<int64_t>(1, std::min<int64_t>(sc.chunks, std::max<int64_t>(M, 1)));
+    c.q = M / k;
+    c.r = M % k;
+    return c;
+}
+
 // demod + fits of C device-resident channel records of bpc buffers each (records ld_c samples apart).
 //   init_dev == nullptr: every cold start uses init[4]; else channel c starts from init_dev[c * init_stride ..+3].
-//   seeded == 0: every buffer is an independent cold start (workers.py:167-173).
-//   seeded != 0: buffer 0 of each channel is fitted cold, buffers 1.. start from its result
-//                (fitters.py:404-417 at n_cores >= nbuf - 1).  seed_row (single-channel slabs only): the row
-//                that already holds that result from an earlier slab.
+//   seed_row (single-channel continuation slabs only): the row that already holds buffer 0's result.
 int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
-                  const double init[4], const double* init_dev, int64_t init_stride, int32_t seeded,
-                  const double* seed_row, const dfk_lm_opts* opts, double* rows, cudaStream_t st,
-                  bool init_is_warm = false) {
+                  const double init[4], const double* init_dev, int64_t init_stride, const Schedule& sc,
+                  const double* seed_row, const dfk_lm_opts* opts, double* rows, cudaStream_t st) {
     const int64_t nbuf = C * bpc;
     if (nbuf == 0) return DFK_OK;
     int rc = ensure(ctx, ctx->qi, static_cast<size_t>(nbuf) * 2 * N * sizeof(double));
@@ -638,7 +709,10 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
     if (rc) return rc;
     double* qi = static_cast<double*>(ctx->qi.ptr);
     double* dc = static_cast<double*>(ctx->dc.ptr);
+    const bool seeded = sc.chunks != 0 && !sc.external_seed;
     const dfk::GuessSrc cold = init_dev ? guess_rows(init_dev, init_stride, bpc, false) : guess_value(init);
+    const dfk::ChainPlan plan = chain_plan(sc, bpc);
+    const dfk::ChainPlan* chain = sc.chunks >= 1 ? &plan : nullptr;
     const bool two_stage = seeded && !seed_row && bpc > 1;
     if (two_stage) {
         // fitters.py:404-405: buffer 0 of every channel is fitted cold before anything else.  Those C fits are a
@@ -668,14 +742,22 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
         rc = launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st, two_stage);
     }
     if (rc) return rc;
+    if (two_stage) DFK_CUDA(cudaStreamWaitEvent(st, ctx->join, 0));  // before the LM timing scope opens
     ProfScope ps(ctx, 1, st);
-    if (!seeded || (bpc == 1 && !seed_row)) return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, cold, dc, opts, rows, st, !init_is_warm);
-    if (seed_row) {  // continuation slab of a single record: everything starts from the stored row
-        return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(seed_row, 0, nbuf, false), dc, opts, rows, st);
-    }
-    DFK_CUDA(cudaStreamWaitEvent(st, ctx->join, 0));
-    // fitters.py:407-417: every other buffer starts from its channel's buffer-0 result
-    return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(rows, bpc * DFK_ROW_STRIDE, bpc, true), dc, opts, rows, st);
+    if (sc.external_seed)  // a slab of a record whose buffer 0 lives elsewhere: init is that buffer's result
+        return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, cold, dc, opts, rows, st, false, chain);
+    if (!seeded || (bpc == 1 && !seed_row)) return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, cold, dc, opts, rows, st, true);
+    if (seed_row)  // continuation slab of a single record: chunk seeds come from the stored row of buffer 0
+        return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(seed_row, 0, nbuf, false), dc, opts, rows, st, false, chain);
+    // fitters.py:407-417: every chunk starts from its channel's buffer-0 result
+    return launch_lm(ctx, qi, nbuf, {1, 0, 1}, N, guess_rows(rows, bpc * DFK_ROW_STRIDE, bpc, true), dc, opts, rows, st,
+                     false, chain);
+}
+
+Schedule schedule_of(int32_t seeded) {
+    Schedule sc;
+    sc.chunks = seeded;
+    return sc;
 }
 
 }  // namespace
@@ -720,6 +802,7 @@ void dfk_default_ekf_opts(dfk_ekf_opts* o) {
         o->q_diag[i] = q[i];
     }
     o->r_val = std::numeric_limits<double>::quiet_NaN();
+    o->init_dc = std::numeric_limits<double>::quiet_NaN();
 }
 
 int dfk_create(int device, dfk_ctx** out) {
@@ -842,20 +925,23 @@ int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, 
     if (rc) return rc;
     if (!init) return fail(DFK_ERR_ARG, "null init");
     if (nbuf > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
-    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, init, nullptr, 0, seeded, nullptr, opts, rows_dev,
-                         ctx->stream());
+    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, init, nullptr, 0, schedule_of(seeded), nullptr, opts,
+                         rows_dev, ctx->stream());
 }
 
 int dfk_nls_fit_seeded_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
-                           const double seed[4], const dfk_lm_opts* opts, double* rows_dev) {
+                           const double seed[4], int32_t chunks, const dfk_lm_opts* opts, double* rows_dev) {
     DFK_ENTER(ctx);
     const int rc = check_nls_args(nbuf, R, N, w0);
     if (rc) return rc;
     if (!seed) return fail(DFK_ERR_ARG, "null seed");
+    if (chunks == 0) return fail(DFK_ERR_ARG, "a seeded slab has at least one chunk (or DFK_SCHED_EACH)");
     if (nbuf > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
-    // every buffer is a warm start from the same 4 values: exactly the "seeded == 0" path with init = seed
-    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, seed, nullptr, 0, 0, nullptr, opts, rows_dev,
-                         ctx->stream(), /*init_is_warm=*/true);
+    Schedule sc;
+    sc.chunks = chunks;
+    sc.external_seed = true;
+    return nls_on_device(ctx, x_dev, 1, nbuf, nbuf * R, R, N, w0, seed, nullptr, 0, sc, nullptr, opts, rows_dev,
+                         ctx->stream());
 }
 
 int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t ld_c,
@@ -871,11 +957,28 @@ int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t 
     if (C * bufs_per_channel > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
     const double zero[4] = {0, 0, 0, 0};
     return nls_on_device(ctx, x_dev, C, bufs_per_channel, ld_c, R, N, w0, init ? init : zero, init_dev, init_stride,
-                         seeded, nullptr, opts, rows_dev, ctx->stream());
+                         schedule_of(seeded), nullptr, opts, rows_dev, ctx->stream());
 }
+
+static int nls_host_impl(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                         const double init[4], Schedule sc, const dfk_lm_opts* opts, double* rows_host);
 
 int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
                      const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_host) {
+    return nls_host_impl(ctx, x_host, nsamp, R, N, w0, init, schedule_of(seeded), opts, rows_host);
+}
+
+int dfk_nls_fit_seeded_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                            const double seed[4], int32_t chunks, const dfk_lm_opts* opts, double* rows_host) {
+    if (chunks == 0) return fail(DFK_ERR_ARG, "a seeded slab has at least one chunk (or DFK_SCHED_EACH)");
+    Schedule sc;
+    sc.chunks = chunks;
+    sc.external_seed = true;
+    return nls_host_impl(ctx, x_host, nsamp, R, N, w0, seed, sc, opts, rows_host);
+}
+
+static int nls_host_impl(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                         const double init[4], Schedule sc, const dfk_lm_opts* opts, double* rows_host) {
     DFK_ENTER(ctx);
     if (nsamp < 0) return fail(DFK_ERR_ARG, "negative sample count");
     const int64_t nbuf = R > 0 ? nsamp / R : 0;
@@ -886,7 +989,8 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
     if (!x_host || !rows_host) return fail(DFK_ERR_ARG, "null host pointer");
     // slabs of whole buffers, ~128 MiB each, double buffered: the copy of slab i+1 overlaps the
     // kernels of slab i.  (A record that fits one slab is a single copy.)
-    const int64_t slab_buffers = std::max<int64_t>(1, std::min<int64_t>(nbuf, (128ll << 20) / (R * 8)));
+    const int64_t slab_target = ctx->host_slab_bytes ? static_cast<int64_t>(ctx->host_slab_bytes) : (128ll << 20);
+    const int64_t slab_buffers = std::max<int64_t>(1, std::min<int64_t>(nbuf, slab_target / (R * 8)));
     const size_t slab_bytes = static_cast<size_t>(slab_buffers) * R * 8;
     const int nslab_bufs = nbuf > slab_buffers ? 2 : 1;
     for (int i = 0; i < nslab_bufs; ++i) {
@@ -905,6 +1009,9 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
     double* rows = static_cast<double*>(ctx->rows.ptr);
     cudaStream_t st = ctx->stream();
     const bool pageable = is_pageable(x_host);
+    HostCallGuard quiesce(ctx);
+    sc.record_buffers = nbuf;
+    const bool seeded = sc.chunks != 0 && !sc.external_seed;
     int64_t done = 0;
     for (int64_t i = 0; done < nbuf; ++i) {
         const int sl = static_cast<int>(i & 1);
@@ -915,7 +1022,8 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
         if (rc) return rc;
         DFK_CUDA(cudaEventRecord(ctx->copied[sl], ctx->copy_stream));
         DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[sl], 0));
-        rc = nls_on_device(ctx, dst, 1, nb, nb * R, R, N, w0, init, nullptr, 0, seeded,
+        sc.b0 = done;
+        rc = nls_on_device(ctx, dst, 1, nb, nb * R, R, N, w0, init, nullptr, 0, sc,
                            (seeded && done > 0) ? rows : nullptr, opts, rows + done * DFK_ROW_STRIDE, st);
         if (rc) return rc;
         DFK_CUDA(cudaEventRecord(ctx->consumed[sl], st));
@@ -924,6 +1032,14 @@ int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t 
     DFK_CUDA(cudaMemcpyAsync(rows_host, rows, static_cast<size_t>(nbuf) * DFK_ROW_STRIDE * sizeof(double),
                              cudaMemcpyDeviceToHost, st));
     DFK_CUDA(cudaStreamSynchronize(st));
+    quiesce.done();
+    return DFK_OK;
+}
+
+int dfk_set_host_slab_bytes(dfk_ctx* ctx, int64_t bytes) {
+    if (!ctx) return fail(DFK_ERR_ARG, "null context");
+    if (bytes < 0) return fail(DFK_ERR_ARG, "negative slab size");
+    ctx->host_slab_bytes = static_cast<size_t>(bytes);
     return DFK_OK;
 }
 
@@ -951,9 +1067,12 @@ int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, 
     if (rc) return rc;
     cudaStream_t st = ctx->stream();
     double* stats = static_cast<double*>(ctx->stats.ptr);
-    if (k0 == 0) {  // initial dc and default measurement variance come from the first (or only) slab
+    const bool need_stats = std::isnan(opts->init_dc) || std::isnan(opts->r_val);
+    if (k0 == 0 && need_stats && !ctx->stats_ready) {
+        // initial dc and default measurement variance come from the first (or only) slab, unless the caller
+        // prepared whole-record moments (dfk_ekf_host on a streamed record)
         const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
-        dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats);
+        dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats, nullptr);
         ctx->launches++;
         DFK_CUDA(cudaGetLastError());
     }
@@ -961,6 +1080,7 @@ int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, 
     a.k0 = k0;
     a.state = state_dev;
     for (int i = 0; i < 4; ++i) a.init[i] = opts->init[i];
+    a.init_dc = opts->init_dc;
     for (int i = 0; i < 5; ++i) {
         a.p0[i] = opts->p0_diag[i];
         a.q[i] = opts->q_diag[i];
@@ -968,13 +1088,24 @@ int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, 
     a.r_val = opts->r_val;
     a.w_m = 2 * dfk::kPi * f_mod;  // fitters.py:262
     a.f_samp = f_samp;
-    const int grid = static_cast<int>((C + dfk::kEkfThreads - 1) / dfk::kEkfThreads);
-    dfk::ekf_kernel<<<grid, dfk::kEkfThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev);
+    // fewest channels per warp that still leaves every warp a scheduler (sub-partition) of its own
+    const int64_t schedulers = static_cast<int64_t>(ctx->sm_count) * 4;
+    int cpw = 1;
+    while (cpw < 32 && (C + cpw - 1) / cpw > schedulers) cpw <<= 1;
+    a.cpw = cpw;
+    const int64_t grid = (C + cpw - 1) / cpw;
+    if (grid > std::numeric_limits<int>::max()) return fail(DFK_ERR_ARG, "too many channels");
+    ProfScope ps(ctx, 3, st);
+    dfk::ekf_kernel<<<static_cast<int>(grid), 32, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
 }
 
+// EKFFitter.fit on host records [C][T].  A record that fits the device goes up whole.  A longer one (cfg 4 is 655 GB)
+// is streamed in slabs of whole buffers, twice when the filter needs the whole-record mean / variance first
+// (fitters.py:253,256 take them over the full record): pass 1 merges per-slab moments, pass 2 runs the filter
+// with its state carried from slab to slab.
 int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64_t R, double f_samp, double f_mod,
                  const dfk_ekf_opts* opts, double* rows_host) {
     DFK_ENTER(ctx);
@@ -982,22 +1113,99 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
     const int64_t nbuf = T / R;
     if (T == 0 || C == 0) return DFK_OK;
     if (!z_host || (nbuf > 0 && !rows_host)) return fail(DFK_ERR_ARG, "null host pointer");
-    int rc = ensure(ctx, ctx->slab[0], static_cast<size_t>(T) * C * 8);
-    if (rc) return rc;
-    rc = ensure(ctx, ctx->rows, std::max<size_t>(8, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8));
-    if (rc) return rc;
+    dfk_ekf_opts d;
+    if (!opts) {
+        dfk_default_ekf_opts(&d);
+        opts = &d;
+    }
+    size_t free_b = 0, total_b = 0;
+    DFK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t rec_bytes = static_cast<size_t>(T) * C * 8;
+    size_t budget = ctx->host_slab_bytes ? 2 * ctx->host_slab_bytes : (free_b + ctx->slab[0].bytes + ctx->slab[1].bytes) / 2;
     cudaStream_t st = ctx->stream();
-    rc = copy_slab_to_device(ctx, ctx->slab[0].ptr, z_host, static_cast<size_t>(T) * C * 8, is_pageable(z_host));
+    int rc = ensure(ctx, ctx->rows, std::max<size_t>(8, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8));
     if (rc) return rc;
-    DFK_CUDA(cudaEventRecord(ctx->copied[0], ctx->copy_stream));
-    DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[0], 0));
-    rc = dfk_ekf_dev(ctx, static_cast<const double*>(ctx->slab[0].ptr), T, C, 1, T, R, f_samp, f_mod, opts,
-                     static_cast<double*>(ctx->rows.ptr));
-    if (rc) return rc;
+    double* rows = static_cast<double*>(ctx->rows.ptr);
+    const bool pageable = is_pageable(z_host);
+    HostCallGuard quiesce(ctx);
+    if (rec_bytes <= budget || nbuf <= 1) {
+        rc = ensure(ctx, ctx->slab[0], rec_bytes);
+        if (rc) return rc;
+        rc = copy_slab_to_device(ctx, ctx->slab[0].ptr, z_host, rec_bytes, pageable);
+        if (rc) return rc;
+        DFK_CUDA(cudaEventRecord(ctx->copied[0], ctx->copy_stream));
+        DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[0], 0));
+        rc = dfk_ekf_dev(ctx, static_cast<const double*>(ctx->slab[0].ptr), T, C, 1, T, R, f_samp, f_mod, opts, rows);
+        if (rc) return rc;
+    } else {
+        // slab = bps buffers of every channel, device layout [C][bps * R]; two slabs alternate
+        int64_t bps = static_cast<int64_t>(budget / 2 / (static_cast<size_t>(C) * R * 8));
+        if (bps < 1) return fail(DFK_ERR_NOMEM, "one buffer of all %lld channels does not fit the device", (long long)C);
+        bps = std::min(bps, nbuf);
+        const int64_t Ts = bps * R;
+        for (int i = 0; i < 2; ++i) {
+            rc = ensure(ctx, ctx->slab[i], static_cast<size_t>(C) * Ts * 8);
+            if (rc) return rc;
+        }
+        rc = ensure(ctx, ctx->misc, static_cast<size_t>(C) * (3 + dfk::kEkfStateStride) * 8 + 256);
+        if (rc) return rc;
+        rc = ensure(ctx, ctx->stats, static_cast<size_t>(C) * 2 * sizeof(double));
+        if (rc) return rc;
+        double* acc = static_cast<double*>(ctx->misc.ptr);
+        double* state = acc + 3 * C;
+        double* slab_rows = nullptr;
+        rc = ensure(ctx, ctx->qi, static_cast<size_t>(C) * bps * DFK_ROW_STRIDE * 8);  // rows of one slab, [C][bps]
+        if (rc) return rc;
+        slab_rows = static_cast<double*>(ctx->qi.ptr);
+        const bool need_stats = std::isnan(opts->init_dc) || std::isnan(opts->r_val);
+        const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
+        int64_t slab_no = 0;
+        for (int pass = need_stats ? 0 : 1; pass < 2; ++pass) {
+            if (pass == 0) DFK_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(C) * 3 * 8, st));
+            // the tail of the record past the last whole buffer only matters to the moments (pass 0)
+            const int64_t t_end = pass == 0 ? T : nbuf * R;
+            for (int64_t t0 = 0; t0 < t_end; t0 += Ts, ++slab_no) {
+                const int sl = static_cast<int>(slab_no & 1);
+                const int64_t tn = std::min(Ts, t_end - t0);
+                double* dst = static_cast<double*>(ctx->slab[sl].ptr);
+                if (slab_no >= 2) DFK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->consumed[sl], 0));
+                // channel c's piece of the slab is contiguous on the host: one strided copy
+                DFK_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(tn) * 8, z_host + t0, static_cast<size_t>(T) * 8,
+                                           static_cast<size_t>(tn) * 8, static_cast<size_t>(C), cudaMemcpyHostToDevice,
+                                           ctx->copy_stream));
+                DFK_CUDA(cudaEventRecord(ctx->copied[sl], ctx->copy_stream));
+                DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[sl], 0));
+                if (pass == 0) {
+                    dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(dst, tn, C, 1, tn, nullptr, acc);
+                    ctx->launches++;
+                    DFK_CUDA(cudaGetLastError());
+                } else {
+                    const int64_t nb = tn / R;
+                    ctx->stats_ready = need_stats;
+                    rc = dfk_ekf_stream_dev(ctx, dst, nb * R, C, 1, tn, R, f_samp, f_mod, opts, t0, state, slab_rows);
+                    ctx->stats_ready = false;
+                    if (rc) return rc;
+                    // rows of this slab [C][nb] -> their place in the [C][nbuf] table
+                    DFK_CUDA(cudaMemcpy2DAsync(rows + (t0 / R) * DFK_ROW_STRIDE, static_cast<size_t>(nbuf) * DFK_ROW_STRIDE * 8,
+                                               slab_rows, static_cast<size_t>(nb) * DFK_ROW_STRIDE * 8,
+                                               static_cast<size_t>(nb) * DFK_ROW_STRIDE * 8, static_cast<size_t>(C),
+                                               cudaMemcpyDeviceToDevice, st));
+                }
+                DFK_CUDA(cudaEventRecord(ctx->consumed[sl], st));
+            }
+            if (pass == 0) {
+                dfk::stats_finish_kernel<<<static_cast<int>((C + 127) / 128), 128, 0, st>>>(
+                    acc, C, static_cast<double*>(ctx->stats.ptr));
+                ctx->launches++;
+                DFK_CUDA(cudaGetLastError());
+            }
+        }
+    }
     if (nbuf > 0)
-        DFK_CUDA(cudaMemcpyAsync(rows_host, ctx->rows.ptr, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8,
+        DFK_CUDA(cudaMemcpyAsync(rows_host, rows, static_cast<size_t>(nbuf) * C * DFK_ROW_STRIDE * 8,
                                  cudaMemcpyDeviceToHost, st));
     DFK_CUDA(cudaStreamSynchronize(st));
+    quiesce.done();
     return DFK_OK;
 }
 
@@ -1065,12 +1273,12 @@ int dfk_profile_enable(dfk_ctx* ctx, int32_t on) {
     return DFK_OK;
 }
 
-int dfk_profile_read(dfk_ctx* ctx, double ms_total[3], int64_t launches[3], int32_t reset) {
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[DFK_PROFILE_KINDS], int64_t launches[DFK_PROFILE_KINDS], int32_t reset) {
     DFK_ENTER(ctx);
     if (!ms_total || !launches) return fail(DFK_ERR_ARG, "null output pointer");
     const int rc = prof_drain(ctx);
     if (rc) return rc;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < DFK_PROFILE_KINDS; ++k) {
         ms_total[k] = ctx->prof_ms[k];
         launches[k] = ctx->prof_n[k];
         if (reset) {
@@ -1107,6 +1315,27 @@ int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out) {
     const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
     *tflops_out = flops / (best_ms * 1e-3) / 1e12;
     return DFK_OK;
+}
+
+int dfk_dev_set(const char* name, int32_t value) {
+    if (!name || !*name || std::strlen(name) >= sizeof(g_dev[0].name)) return fail(DFK_ERR_ARG, "bad override name");
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    const int n = g_dev_count.load(std::memory_order_relaxed);
+    for (int i = 0; i < n; ++i)
+        if (std::strcmp(g_dev[i].name, name) == 0) {
+            g_dev[i].value = value;
+            return DFK_OK;
+        }
+    if (n == static_cast<int>(sizeof(g_dev) / sizeof(g_dev[0]))) return fail(DFK_ERR_ARG, "override table full");
+    std::strcpy(g_dev[n].name, name);
+    g_dev[n].value = value;
+    g_dev_count.store(n + 1, std::memory_order_release);
+    return DFK_OK;
+}
+
+void dfk_dev_clear(void) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    g_dev_count.store(0, std::memory_order_release);
 }
 
 int64_t dfk_launch_count(dfk_ctx* ctx) { return ctx ? ctx->launches : 0; }

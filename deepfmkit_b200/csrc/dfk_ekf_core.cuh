@@ -1,6 +1,21 @@
 // One predict+update step of the 5-state DFMI EKF (reference loop body fitters.py:274-302).
-// State x = [a, m, phi, psi, dc], full 5x5 covariance (the reference's simple-form update does not
-// keep P symmetric, so no symmetry is assumed), scalar measurement.
+// State x = [a, m, phi, psi, dc], scalar measurement z_k = a cos(phi + m cos(w_m t_k + psi)) + dc.
+//
+// The step is a ~35-operation dependent chain (psi -> theta -> sincos -> arg -> sincos -> P H^T -> S -> 1/S -> x),
+// and with a few thousand channels there is at most one warp per SM sub-partition, so throughput is set by the
+// latency of that chain and by the number of fp64 instructions a warp issues per step (measured on B200,
+// benchmarks/micro/fp64_micro.cu: 8.7 cycles per dependent DFMA, 2.13 issue cycles per warp-wide fp64 instruction
+// whatever the number of active lanes, 224 cycles per library sincos, 72 per division).  Hence:
+//   * sincos_cw: Cody-Waite reduction (exact for |x| < 1e6) + fdlibm's minimax kernels in Estrin form -- 9 dependent
+//     operations instead of ~26; the library routine remains for larger arguments;
+//   * the Jacobian row is H = [ca, sa g1, sa g2, sa g3, 1] with g = (-a ct, -a, a m st) known before sincos(arg)
+//     returns, so P H^T = (P_i0 ca + P_i4) + sa (P_i1 g1 + P_i2 g2 + P_i3 g3) is two operations deep once sa, ca
+//     arrive, the bracket being formed in the shadow of the second sincos;
+//   * 1/S by rcp.approx + two Newton steps (<= 1 ulp); t_k = k / f_samp by a Markstein-corrected product (bit-equal
+//     to the IEEE quotient numpy forms, fitters.py:263);
+//   * P is carried as its upper triangle.  The reference's simple-form update P <- (I - K H) P keeps P symmetric up
+//     to rounding only; carrying the triangle differs from it by that rounding noise, which the filter contracts
+//     (measured deviation of the states from the reference loop: tests/test_host_cores.py).
 #pragma once
 #include "dfk_common.cuh"
 
@@ -23,72 +38,136 @@ DFK_HD double add_rn(double a, double b) {
 #endif
 }
 
+// sin and cos of x to <= 1 ulp-level absolute error (1.2e-16) for |x| < 1e6.
+// n = rint(x 2/pi) by the 1.5 2^52 trick; r = x - n pi/2 with pi/2 = c1 + c2, c1 holding 33 bits so that n c1 is
+// exact for n < 2^20; sin r and cos r by the fdlibm minimax polynomials on |r| <= pi/4, evaluated pairwise.
+DFK_HD void sincos_cw(double x, double* s, double* c) {
+    if (!(fabs(x) < 1.0e6)) {  // large, inf or NaN: the library's Payne-Hanek path
+        sincos_hd(x, s, c);
+        return;
+    }
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(x, 6.36619772367581382433e-01, kMagic);
+    const double n = t - kMagic;
+#if defined(__CUDA_ARCH__)
+    const int q = __double2loint(t);
+#else
+    long long bits;
+    __builtin_memcpy(&bits, &t, 8);
+    const int q = static_cast<int>(bits & 0xffffffffll);
+#endif
+    double r = fma(-n, 1.57079632673412561417e+00, x);
+    r = fma(-n, 6.07710050650619224932e-11, r);
+    const double z = r * r;
+    const double z2 = z * z, r3 = r * z;
+    const double s01 = fma(8.33333333332248946124e-03, z, -1.66666666666666324348e-01);
+    const double s23 = fma(2.75573137070700676789e-06, z, -1.98412698298579493134e-04);
+    const double s45 = fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
+    const double c01 = fma(-1.38888888888741095749e-03, z, 4.16666666666666019037e-02);
+    const double c23 = fma(-2.75573143513906633035e-07, z, 2.48015872894767294178e-05);
+    const double c45 = fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
+    const double z4 = z2 * z2;
+    const double half = fma(-0.5, z, 1.0);
+    const double sp = fma(s45, z4, fma(s23, z2, s01));
+    const double cp = fma(c45, z4, fma(c23, z2, c01));
+    const double sr = fma(r3, sp, r);
+    const double cr = fma(z2, cp, half);
+    const double a = (q & 1) ? cr : sr;
+    const double b = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -a : a;
+    *c = ((q + 1) & 2) ? -b : b;
+}
+
+// 1 / s to <= 1 ulp for normal s of ordinary magnitude; anything else goes to the IEEE division.
+DFK_HD double recip(double s) {
+#if defined(__CUDA_ARCH__)
+    const double as = fabs(s);
+    if (!(as > 1.0e-290 && as < 1.0e290)) return 1.0 / s;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    double e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-s, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / s;
+#endif
+}
+
 struct EkfState {
     double x[5];
-    double P[5][5];
+    // upper triangle of the covariance, row by row: 00 01 02 03 04 | 11 12 13 14 | 22 23 24 | 33 34 | 44
+    double P[15];
 };
 
+DFK_HD int tri(int i, int j) {  // index of P_ij, i <= j
+    return i * 5 - (i * (i - 1)) / 2 + (j - i);
+}
+
 struct EkfConsts {
-    double w_m;     // 2*pi*f_mod            (fitters.py:262)
-    double f_samp;  // t_k = k / f_samp      (fitters.py:263)
-    double q[5];    // process noise diagonal
-    double r;       // measurement variance
+    double w_m;       // 2*pi*f_mod            (fitters.py:262)
+    double f_samp;    // t_k = k / f_samp      (fitters.py:263)
+    double inv_fs;    // fl(1 / f_samp)
+    double q[5];      // process noise diagonal
+    double r;         // measurement variance
 };
+
+// fl(kd / f_samp): a Markstein correction of the product with the rounded reciprocal.
+DFK_HD double sample_time(double kd, const EkfConsts& c) {
+    const double q0 = kd * c.inv_fs;
+    const double rem = fma(-q0, c.f_samp, kd);
+    return fma(rem, c.inv_fs, q0);
+}
 
 // Sample index k is absolute: unlike the NLS lock-in, the EKF phase never restarts (fitters.py:280).
 // kd: the absolute sample index as a double (exact for every index below 2^53).
 DFK_HD void ekf_step(EkfState& s, double z, double kd, const EkfConsts& c) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) s.P[i][i] += c.q[i];  // P = F P F^T + Q with F = I (fitters.py:276)
+    double* P = s.P;
+    // P = F P F^T + Q with F = I (fitters.py:276)
+    P[0] += c.q[0]; P[5] += c.q[1]; P[9] += c.q[2]; P[12] += c.q[3]; P[14] += c.q[4];
 
     const double a = s.x[0], m = s.x[1], phi = s.x[2], psi = s.x[3], dc = s.x[4];
-    // the angle is formed exactly as numpy does, w_m * (k / f_samp) + psi, each operation rounded once:
-    // at t ~ 100 s its rounding (1e-10 rad) is the largest noise term the filter sees from arithmetic.
-    const double t = kd / c.f_samp;
-    const double theta = add_rn(mul_rn(c.w_m, t), psi);
+    // the carrier angle is formed exactly as numpy does, w_m * (k / f_samp) + psi, each operation rounded once:
+    // at t ~ 100 s its rounding (1e-10 rad) is the largest arithmetic noise the filter sees.
+    const double theta = add_rn(mul_rn(c.w_m, sample_time(kd, c)), psi);
     double st, ct;
-    sincos_hd(theta, &st, &ct);
-    const double arg = add_rn(phi, mul_rn(m, ct));
+    sincos_cw(theta, &st, &ct);
+    const double arg = fma(m, ct, phi);  // fitters.py:281
+    // Jacobian row (fitters.py:287-293) without its common factor sin(arg): H = [ca, sa g1, sa g2, sa g3, 1]
+    const double g1 = -(a * ct), g2 = -a, g3 = (a * m) * st;
+    // rows of P (symmetric): G_i = P_i1 g1 + P_i2 g2 + P_i3 g3, formed while sincos(arg) is in flight
+    const double G0 = fma(P[3], g3, fma(P[2], g2, P[1] * g1));
+    const double G1 = fma(P[7], g3, fma(P[6], g2, P[5] * g1));
+    const double G2 = fma(P[10], g3, fma(P[9], g2, P[6] * g1));
+    const double G3 = fma(P[12], g3, fma(P[10], g2, P[7] * g1));
+    const double G4 = fma(P[13], g3, fma(P[11], g2, P[8] * g1));
     double sa, ca;
-    sincos_hd(arg, &sa, &ca);
-    const double pred = a * ca + dc;
-    const double H[5] = {ca, -a * sa * ct, -a * sa, a * m * sa * st, 1.0};  // fitters.py:287-293
-    const double innov = z - pred;
-
-    double PHt[5];
-    double S = c.r;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) acc += s.P[i][j] * H[j];
-        PHt[i] = acc;
-    }
-    double hph = 0.0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) hph += H[i] * PHt[i];
-    S += hph;
-    const double invS = 1.0 / S;  // np.linalg.inv of the 1x1 innovation covariance (fitters.py:298)
-    double K[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) K[i] = PHt[i] * invS;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) s.x[i] += K[i] * innov;
-
-    double HP[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < 5; ++l) acc += H[l] * s.P[l][j];
-        HP[j] = acc;
-    }
-    // P = (I - K H) P = P - K (H P)  (fitters.py:302, simple form, not Joseph)
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-#pragma unroll
-        for (int j = 0; j < 5; ++j) s.P[i][j] -= K[i] * HP[j];
-    }
+    sincos_cw(arg, &sa, &ca);
+    const double innov = z - fma(a, ca, dc);  // fitters.py:283,296
+    // P H^T
+    const double h0 = fma(sa, G0, fma(P[0], ca, P[4]));
+    const double h1 = fma(sa, G1, fma(P[1], ca, P[8]));
+    const double h2 = fma(sa, G2, fma(P[2], ca, P[11]));
+    const double h3 = fma(sa, G3, fma(P[3], ca, P[13]));
+    const double h4 = fma(sa, G4, fma(P[4], ca, P[14]));
+    // S = H P H^T + R (fitters.py:297)
+    const double inner = fma(g2, h2, g1 * h1) + g3 * h3;
+    const double S = fma(sa, inner, fma(ca, h0, h4 + c.r));
+    const double invS = recip(S);  // np.linalg.inv of the 1x1 innovation covariance (fitters.py:298)
+    const double gain = innov * invS;
+    s.x[0] = fma(h0, gain, a);
+    s.x[1] = fma(h1, gain, m);
+    s.x[2] = fma(h2, gain, phi);
+    s.x[3] = fma(h3, gain, psi);
+    s.x[4] = fma(h4, gain, dc);
+    // P = (I - K H) P = P - K (H P), H P = (P H^T)^T for the symmetric P (fitters.py:302, simple form, not Joseph)
+    const double k0 = h0 * invS, k1 = h1 * invS, k2 = h2 * invS, k3 = h3 * invS, k4 = h4 * invS;
+    P[0] = fma(-k0, h0, P[0]); P[1] = fma(-k0, h1, P[1]); P[2] = fma(-k0, h2, P[2]); P[3] = fma(-k0, h3, P[3]);
+    P[4] = fma(-k0, h4, P[4]);
+    P[5] = fma(-k1, h1, P[5]); P[6] = fma(-k1, h2, P[6]); P[7] = fma(-k1, h3, P[7]); P[8] = fma(-k1, h4, P[8]);
+    P[9] = fma(-k2, h2, P[9]); P[10] = fma(-k2, h3, P[10]); P[11] = fma(-k2, h4, P[11]);
+    P[12] = fma(-k3, h3, P[12]); P[13] = fma(-k3, h4, P[13]);
+    P[14] = fma(-k4, h4, P[14]);
 }
 
 }  // namespace dfk

@@ -37,6 +37,25 @@ struct FitMap {
     long long row_mul;       // its result row is rows[u * row_mul]  (1 unless qi is a compacted subset)
 };
 
+// The reference's warm-start schedule (fitters.py:370-428).  Buffer 0 of a record is fitted from the user's guess;
+// the M buffers after it are cut into k chunks (np.array_split: r chunks of q + 1 buffers, then k - r of q); the first
+// buffer of a chunk starts from buffer 0's result, every other buffer from its predecessor's.  k = 1 is also the
+// sequential mode (parallel=False).  Unit u of a launch is buffer b0 + u % bpc of channel u / bpc.
+struct ChainPlan {
+    long long bpc;    // buffers per channel in this launch
+    long long b0;     // index within the record of the launch's first buffer (host slabs: buffers already done)
+    long long first;  // first chained buffer of a record: 1 (buffer 0 is the cold fit) or 0 (the seed comes from elsewhere)
+    long long q, r;   // chunk sizes (q == 0: every buffer is its own chunk)
+};
+
+DFK_HD bool chunk_start(const ChainPlan& c, long long record_buffer) {
+    const long long i = record_buffer - c.first;
+    if (i < 0) return true;  // the cold buffer itself
+    if (c.q == 0) return true;
+    const long long head = c.r * (c.q + 1);
+    return i < head ? (i % (c.q + 1)) == 0 : ((i - head) % c.q) == 0;
+}
+
 DFK_D void flush_counts(const LmCounts& c, LmCounts* global, bool leader) {
     // leaders of each group hold the counts; sum over the warp, one atomic per counter per warp
     unsigned long long v[5] = {leader ? c.n_state : 0ull, leader ? c.n_ssq : 0ull, leader ? c.n_solve : 0ull,
@@ -62,7 +81,8 @@ __global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __res
                                                               int N, GuessSrc guess, const double* __restrict__ dc,
                                                               LmOpts o, double* rows,
                                                               int* __restrict__ retry_list, int* __restrict__ retry_count,
-                                                              LmCounts* __restrict__ counts) {
+                                                              LmCounts* __restrict__ counts,
+                                                              int* __restrict__ parked_flags) {
     extern __shared__ double bes_smem[];
     constexpr int kFitsPerBlock = TPB / G;
     const int group = threadIdx.x / G;
@@ -100,10 +120,83 @@ __global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __res
             row[5] = ssq;
             row[6] = done ? 0.0 : -1.0;  // -1: parked for the retry stage
             row[7] = static_cast<double>(steps);
-            if (!done) retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
+            if (parked_flags) {  // chain schedule: lm_chain_kernel walks the parked runs
+                parked_flags[u] = done ? 0 : 1;
+            } else if (!done) {
+                retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
+            }
         }
     }
     flush_counts(cnt, counts, rank == 0);
+}
+
+// Second stage of the chain schedule.  The first stage started every buffer from its chunk's seed (buffer 0's
+// result); on a stationary record that converges everywhere and this kernel finds nothing to do.  Where the
+// parameters drift along the record the first descent of later buffers fails (parked), while the reference, whose
+// warm start moves along with the record, keeps converging.  Here a warp takes each maximal run of parked buffers
+// inside a chunk and walks it in order, fitting each buffer from its predecessor's final result exactly as
+// fitters.py:42-58 does (first descent, grid fallback if that fails, fit.py:322-362).  A parked buffer that opens a
+// chunk already had the reference's start (the chunk seed), so it continues with the fallback alone.
+// Buffers that converged in the first stage are taken to be where the chain would have put them: the same minimum,
+// reached from a different start (the schedules agree to <= 1e-10 on such buffers).
+__global__ void __launch_bounds__(kLmThreads) lm_chain_kernel(const double* __restrict__ qi, long long nfit, int N,
+                                                              LmOpts o, ChainPlan plan, double* rows,
+                                                              const int* __restrict__ parked,
+                                                              LmCounts* __restrict__ counts) {
+    extern __shared__ double bes_smem[];
+    double* bes = bes_smem + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * kLmThreads + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * kLmThreads) >> 5;
+    LmCounts cnt = {};
+    for (long long base = warp * 32; base < nfit; base += nwarps * 32) {
+        const long long u = base + lane;
+        bool opens = false;
+        if (u < nfit && parked[u]) {
+            const long long b = u % plan.bpc;
+            opens = b == 0 || chunk_start(plan, plan.b0 + b) || !parked[u - 1];
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, opens);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            long long v = base + l;  // first buffer of the run
+            double p[4];
+            bool have_prev = false;
+            while (true) {
+                const long long b = v % plan.bpc;
+                double* row = rows + v * kRowStride;
+                const double* q = qi + v * 2 * N;
+                const bool start = chunk_start(plan, plan.b0 + b);
+                double ssq;
+                int steps, status;
+                __syncwarp();
+                if (start) {  // first descent from the chunk seed was stage 1: continue with the fallback
+                    p[0] = row[0]; p[1] = row[1]; p[2] = row[2]; p[3] = row[3];
+                    ssq = row[5];
+                    steps = static_cast<int>(row[7]);
+                    status = retry_fit<32>(N, q, 1, bes, kLmThreads, o, p, ssq, steps, cnt);
+                    normalise_params(p);
+                } else {
+                    if (!have_prev) {
+                        const double* prev = row - kRowStride;  // final: it converged in stage 1 or belongs to an earlier launch
+                        p[0] = prev[0]; p[1] = prev[1]; p[2] = prev[2]; p[3] = prev[3];
+                    }
+                    status = fit_full<32>(N, q, 1, bes, kLmThreads, o, p, ssq, steps, cnt);
+                }
+                if (lane == 0) {
+                    row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
+                    row[5] = ssq;
+                    row[6] = static_cast<double>(status);
+                    row[7] = static_cast<double>(steps);
+                }
+                have_prev = true;
+                ++v;
+                if (v >= nfit || (v % plan.bpc) == 0 || !parked[v] || chunk_start(plan, plan.b0 + v % plan.bpc)) break;
+            }
+        }
+    }
+    flush_counts(cnt, counts, lane == 0);
 }
 
 // Bulk variant of stage 1 for one thread per fit: the LM driver of fit.py:208-258 flattened into a per-lane state

@@ -8,10 +8,13 @@ once and three kernels demodulate and fit every buffer.  There is no CPU path he
 
 Schedule.  The reference's parallel mode fits buffer 0 from the user's initial guess and seeds every
 chunk of the remaining buffers with that result (fitters.py:404-417); within a chunk the warm start
-chains from buffer to buffer.  The GPU runs the reference's own schedule at ``n_cores >= nbuf - 1``:
-every buffer after the first starts from buffer 0's result.  ``parallel`` and ``n_cores`` are accepted
-and ignored; ``parallel=False`` (one sequential warm-start chain) is served by the same
-schedule -- the solutions agree to <= 1e-10, far inside the 1e-8 gate.
+chains from buffer to buffer, and ``parallel=False`` is one chain over the whole record
+(fitters.py:370-393).  ``parallel`` and ``n_cores`` keep that meaning here: they select the chunking
+(``n_cores`` defaults to ``os.cpu_count()`` as in the reference).  On the GPU every buffer is first
+fitted from its chunk's seed in one launch; on a stationary record that is the whole job (the schedules
+agree to <= 1e-10 there).  Buffers whose first descent fails -- a record whose phase walks away from
+buffer 0 -- are then walked in record order from their predecessor's result, as the chain does
+(``lm_chain_kernel``), so flags and parameters follow the reference's schedule on drifting records too.
 
 Additive API for what the reference can only do in a Python loop: :func:`nls_fit_batch` (many channels
 / Monte-Carlo realisations in one launch) and :func:`ekf_fit_batch`.
@@ -19,6 +22,7 @@ Additive API for what the reference can only do in a Python loop: :func:`nls_fit
 from __future__ import annotations
 
 import logging
+import os
 from abc import ABC, abstractmethod
 
 import numpy as np
@@ -89,7 +93,10 @@ class StandardNLSFitter(BaseFitter):
         init_m = kwargs.get("init_m", 6.0)
         init_psi = kwargs.get("init_psi", 0.0)
         device = kwargs.get("device", 0)
-        # accepted for compatibility, meaningless on the GPU: parallel, n_cores, verbose
+        # fitters.py:356-368: parallel=True -> n_cores chunks (default: every core), parallel=False -> one chain
+        parallel = kwargs.get("parallel", True)
+        n_cores = kwargs.get("n_cores", None)
+        chunks = max(1, int(n_cores if n_cores is not None else (os.cpu_count() or 1))) if parallel else 1
 
         R, _, nbuf = _calculate_fit_params(main_raw, n)
         if nbuf == 0:
@@ -97,7 +104,7 @@ class StandardNLSFitter(BaseFitter):
         x = _record_values(main_raw)[: nbuf * R]  # the reference's reshape(-1, R) raises on a ragged tail (Q7)
         w0 = 2.0 * np.pi * main_raw.f_mod / main_raw.f_samp  # fitters.py:39
         ctx = _lib.get_context(device)
-        rows = ctx.nls_fit_host(x, R, int(ndata), w0, [init_a, init_m, 0.0, init_psi], seeded=True,
+        rows = ctx.nls_fit_host(x, R, int(ndata), w0, [init_a, init_m, 0.0, init_psi], seeded=chunks,
                                 opts=fit_tunables.current_lm_opts(kwargs.get("tunables_from")))
         return rows_to_frame(rows)
 
@@ -140,6 +147,8 @@ def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_ps
     x: ``[C, T]`` float64 -- a numpy array (copied to the GPU) or a CUDA torch tensor (used in place).
     init_m (and init_a, init_psi) may be scalars or length-C arrays (per-channel cold starts, the CRLB
     sweep recipe of workers.py:167-173 with ``seeded=False`` and one buffer per realisation).
+    seeded: False -> independent cold starts; True -> every buffer from its channel's buffer 0; an int k ->
+    the reference's k-chunk chain schedule per channel (1 = ``parallel=False``).
     Returns rows ``[C, nbuf, 8]`` = amp, m, phi, psi, dc, ssq, fitok, accepted LM steps.
     """
     import torch

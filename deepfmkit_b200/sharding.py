@@ -2,7 +2,7 @@
 
 The readout path has no exchange step: every buffer / channel is independent.  A record
 is cut into contiguous time slabs aligned to buffer boundaries, one per rank; the only shared datum is
-the 4-double seed from buffer 0 (fitters.py:404-417), which rank 0 computes and broadcasts.  Result rows
+the 4-double seed from buffer 0 (fitters.py:404-417): rank 0 fits that one buffer and broadcasts the result.  Result rows
 are gathered on rank 0 in slab order.  One process per GPU; ``torch.distributed`` (nccl on the GPU box,
 gloo in the CPU tests) is used only for that broadcast and the final gather of the small row table.
 """
@@ -59,15 +59,19 @@ def gather_rows(local_rows: np.ndarray, n_units: int, dst: int = 0, group=None):
     return np.concatenate(parts, axis=0)
 
 
-def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, group=None, tunables_from=None):
+def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, group=None, tunables_from=None,
+                    chunks_per_rank=1, gather=True):
     """NLS readout of one long record sharded over the ranks of ``group`` as contiguous buffer-aligned slabs.
 
     Every rank calls this with *its* slab: ``x_slab`` holds buffers ``slab_bounds(n_buffers_total, world, rank)``
-    of the record (a CUDA float64 tensor, or a numpy array that is copied to this rank's GPU).  Rank 0 fits
-    buffer 0 from ``init`` (fitters.py:404-405) inside its own slab; the fitted [amp, m, phi, psi] is broadcast
-    (32 bytes) and every other slab starts all its buffers from it (fitters.py:407-417).  No other exchange:
-    the kernels of different ranks never communicate.  Returns the full ``[n_buffers_total, 8]`` row table on
-    rank 0 (None elsewhere).
+    of the record -- a CUDA float64 tensor (used in place) or a host numpy array (streamed through the library's
+    staged host path, slab copies overlapping the kernels).  Rank 0 fits buffer 0 *alone* from ``init``
+    (fitters.py:404-405: one demodulation + one cold fit, well under a millisecond) and the fitted
+    [amp, m, phi, psi] is broadcast (32 bytes); then all ranks, rank 0 included, fit their slabs concurrently as
+    ``chunks_per_rank`` chains started from that seed (fitters.py:407-417 -- a rank boundary is a chunk boundary,
+    i.e. the reference's pool schedule with ``n_cores = world * chunks_per_rank``).  No other exchange: the kernels
+    of different ranks never communicate.  Returns the full ``[n_buffers_total, 8]`` row table on rank 0 (None
+    elsewhere), or with ``gather=False`` this rank's own rows.
     """
     import torch
     import torch.distributed as dist
@@ -80,26 +84,48 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
     if device is None:
         device = torch.cuda.current_device()
     dev = torch.device("cuda", device)
-    xt = x_slab if isinstance(x_slab, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_slab, dtype=np.float64))
-    xt = xt.to(dev).contiguous().view(-1)
-    if xt.numel() < nb * R:
-        raise ValueError(f"rank {rank}: slab holds {xt.numel()} samples, needs {nb * R}")
     ctx = _lib.get_context(device)
     opts = fit_tunables.current_lm_opts(tunables_from)
-    rows = torch.zeros((nb, _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
-        ctx.use_torch_stream()
-        try:
+    on_device = isinstance(x_slab, torch.Tensor) and x_slab.is_cuda
+    first = 1 if rank == 0 else 0  # rank 0's slab opens with buffer 0, which is fitted cold
+    if on_device:
+        xt = x_slab.contiguous().view(-1)
+        if xt.numel() < nb * R:
+            raise ValueError(f"rank {rank}: slab holds {xt.numel()} samples, needs {nb * R}")
+        rows = torch.zeros((nb, _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            ctx.use_torch_stream()
+            try:
+                seed_local = np.zeros(4)
+                if rank == 0 and nb > 0:
+                    ctx.nls_fit_dev(xt.data_ptr(), 1, R, ndata, w0, init, _lib.SCHED_EACH, opts, rows.data_ptr())
+                    torch.cuda.current_stream(dev).synchronize()
+                    seed_local = rows[0, :4].cpu().numpy()
+                seed = broadcast_seed(seed_local, src=0, group=group)
+                if nb - first > 0:
+                    ctx.nls_fit_seeded_dev(xt.data_ptr() + first * R * 8, nb - first, R, ndata, w0, seed, opts,
+                                           rows.data_ptr() + first * _lib.ROW_STRIDE * 8, chunks=chunks_per_rank)
+                torch.cuda.current_stream(dev).synchronize()
+            finally:
+                ctx.use_default_stream()
+        local = rows.cpu().numpy()
+    else:
+        xs = np.ascontiguousarray(np.asarray(x_slab, dtype=np.float64)).reshape(-1)
+        if xs.size < nb * R:
+            raise ValueError(f"rank {rank}: slab holds {xs.size} samples, needs {nb * R}")
+        local = np.zeros((nb, _lib.ROW_STRIDE))
+        seed_local = np.zeros(4)
+        with torch.cuda.device(dev):
             if rank == 0 and nb > 0:
-                ctx.nls_fit_dev(xt.data_ptr(), nb, R, ndata, w0, init, True, opts, rows.data_ptr())
-            torch.cuda.current_stream(dev).synchronize()
-            seed = broadcast_seed(rows[0, :4].cpu().numpy() if rank == 0 and nb > 0 else np.zeros(4), src=0, group=group)
-            if rank != 0 and nb > 0:
-                ctx.nls_fit_seeded_dev(xt.data_ptr(), nb, R, ndata, w0, seed, opts, rows.data_ptr())
-            torch.cuda.current_stream(dev).synchronize()
-        finally:
-            ctx.use_default_stream()
-    return gather_rows(rows.cpu().numpy(), n_buffers_total, dst=0, group=group)
+                local[:1] = ctx.nls_fit_host(xs[:R], R, ndata, w0, init, seeded=True, opts=opts)
+                seed_local = local[0, :4].copy()
+            seed = broadcast_seed(seed_local, src=0, group=group)
+            if nb - first > 0:
+                local[first:] = ctx.nls_fit_seeded_host(xs[first * R: nb * R], R, ndata, w0, seed, chunks=chunks_per_rank,
+                                                        opts=opts)
+    if not gather:
+        return local
+    return gather_rows(local, n_buffers_total, dst=0, group=group)
 
 
 def ekf_fit_sharded(z_channels, n_channels_total, f_samp, f_mod, n, device=None, group=None, **ekf_kwargs):

@@ -30,9 +30,23 @@
 extern "C" {
 #endif
 
-#define DFK_ABI_VERSION 1
+#define DFK_ABI_VERSION 2
 #define DFK_ROW_STRIDE 8
 #define DFK_MAX_HARMONICS 64
+
+#define DFK_PROFILE_KINDS 4
+
+/* Warm-start schedule of a record, the `seeded` argument of the NLS entries (fitters.py:370-428):
+ *   DFK_SCHED_INDEPENDENT  every buffer is a cold start from init (single-buffer fits, workers.py:167-173)
+ *   k >= 1                 buffer 0 from init; the buffers after it in k chunks (np.array_split), the first buffer of
+ *                          a chunk started from buffer 0's result, every other from its predecessor's result:
+ *                          StandardNLSFitter.fit(parallel=True, n_cores=k) (fitters.py:395-428); k = 1 is also the
+ *                          sequential chain of parallel=False (fitters.py:370-393)
+ *   DFK_SCHED_EACH         every buffer its own chunk (the pool schedule at n_cores >= nbuf - 1)
+ * On the GPU all buffers are first fitted from their chunk's seed at once; buffers whose first descent fails are
+ * then walked in record order from their predecessor's result, which is what the chain would have done. */
+#define DFK_SCHED_INDEPENDENT 0
+#define DFK_SCHED_EACH (-1)
 
 #define DFK_OK 0
 #define DFK_ERR_ARG (-1)
@@ -60,6 +74,7 @@ typedef struct dfk_ekf_opts {
     double p0_diag[5];  /* initial covariance diagonal           (1,1,1,1,1)      */
     double q_diag[5];   /* process noise diagonal (1e-8,1e-8,1e-6,1e-6,1e-8)      */
     double r_val;       /* measurement variance; NaN = var(record) per channel (fitters.py:256) */
+    double init_dc;     /* initial dc state; NaN = mean(record) per channel (fitters.py:253)    */
 } dfk_ekf_opts;
 
 /* Work counters of the LM kernels (for the FP64 flop accounting in bench.py). */
@@ -106,18 +121,18 @@ int dfk_demod(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_
 int dfk_lm_fit(dfk_ctx* ctx, const double* qi_dev, int64_t nbuf, int32_t N, const double* guess_dev,
                int64_t guess_stride, const double* dc_dev, const dfk_lm_opts* opts, double* rows_dev);
 
-/* Whole NLS readout of one device-resident record: demod, fit buffer 0 from init, fit buffers
- * 1.. seeded from buffer 0's result.  Replaces StandardNLSFitter._fit_parallel and its
- * multiprocessing.Pool (fitters.py:395-428) at n_cores >= nbuf.  seeded == 0 fits every buffer
- * from init (independent single-buffer fits, workers.py:167-173). */
+/* Whole NLS readout of one device-resident record: demod, fit buffer 0 from init, fit the other
+ * buffers on the schedule `seeded` names (DFK_SCHED_* above).  Replaces StandardNLSFitter._fit_sequential
+ * (fitters.py:370-393) and _fit_parallel with its multiprocessing.Pool (fitters.py:395-428). */
 int dfk_nls_fit_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
                     const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
 
-/* A slab of a record whose buffer 0 lives elsewhere (another GPU): every buffer of the slab starts from
- * seed[4], the fitted [amp, m, phi, psi] of the record's buffer 0 -- what each Pool chunk receives as
- * seed_guess in fitters.py:407-417.  Slabs are independent: no inter-GPU traffic on the kernel path. */
+/* A slab of a record whose buffer 0 lives elsewhere (another GPU): the slab is `chunks` chunks (>= 1, or
+ * DFK_SCHED_EACH) whose first buffers start from seed[4], the fitted [amp, m, phi, psi] of the record's
+ * buffer 0 -- what each Pool chunk receives as seed_guess in fitters.py:407-417.  Slabs are independent:
+ * no inter-GPU traffic on the kernel path. */
 int dfk_nls_fit_seeded_dev(dfk_ctx* ctx, const double* x_dev, int64_t nbuf, int64_t R, int32_t N, double w0,
-                           const double seed[4], const dfk_lm_opts* opts, double* rows_dev);
+                           const double seed[4], int32_t chunks, const dfk_lm_opts* opts, double* rows_dev);
 
 /* The same for C channel records at once (additive API for multi-channel batches and Monte-Carlo
  * sweeps; the reference loops dff.fit(label) per channel, core.py:279-286).  Channel c is the
@@ -138,9 +153,11 @@ int dfk_ekf_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t
 
 /* The same filter fed slab by slab, for records that do not fit the GPU (cfg 4: 655 GB): samples
  * k0 .. k0+T-1 of every channel per call, k0 and T multiples of R.  state_dev (C x 32 doubles: x[5],
- * P[25], r) carries the filter between calls; the call with k0 == 0 initialises it (initial dc and the
- * default measurement variance then come from this first slab instead of the whole record, the one
- * place the slab-wise result departs from EKFFitter.fit on the full record).
+ * the upper triangle of P [15], r at index 30) carries the filter between calls; the call with k0 == 0
+ * initialises it.  Initial dc and the default measurement variance are those of opts (init_dc, r_val);
+ * where opts leaves them NaN they come from this first slab instead of the whole record -- the one
+ * place the slab-wise result can depart from EKFFitter.fit on the full record (dfk_ekf_host computes the
+ * whole-record moments in a first pass instead).
  * rows_dev: C x (T/R) x DFK_ROW_STRIDE for this slab. */
 int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c,
                        int64_t R, double f_samp, double f_mod, const dfk_ekf_opts* opts, int64_t k0,
@@ -167,23 +184,40 @@ int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, in
 int dfk_nls_fit_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
                      const double init[4], int32_t seeded, const dfk_lm_opts* opts, double* rows_host);
 
-/* EKFFitter.fit on host records, channel-major [C][T]. rows_host: C x (T/R) x DFK_ROW_STRIDE. */
+/* dfk_nls_fit_seeded_dev for a host slab (same streaming as dfk_nls_fit_host): what each rank of a record sharded
+ * over several GPUs calls on its own slab once buffer 0's result is known. */
+int dfk_nls_fit_seeded_host(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
+                            const double seed[4], int32_t chunks, const dfk_lm_opts* opts, double* rows_host);
+
+/* EKFFitter.fit on host records, channel-major [C][T]. rows_host: C x (T/R) x DFK_ROW_STRIDE.
+ * A record larger than the device is streamed in slabs of whole buffers (twice when the whole-record
+ * mean / variance are needed first), the filter state carried on the device from slab to slab. */
 int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64_t R, double f_samp,
                  double f_mod, const dfk_ekf_opts* opts, double* rows_host);
+
+/* Slab size of the two host-pointer entries above (0 restores the defaults: 128 MiB NLS slabs, half the free
+ * device memory for the EKF).  Lets a small record exercise the streaming path. */
+int dfk_set_host_slab_bytes(dfk_ctx* ctx, int64_t bytes);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 /* Counters accumulated by the LM kernels since the last reset (device -> host copy, syncs). */
 int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset);
-/* Device-time accounting per kernel class for the roofline report: with profiling on, the NLS entry
- * points record CUDA event pairs on the launching stream around the demodulation launch (index 0) and
- * around the LM launches (index 1), and on the side stream around the cold seed fits that overlap the
- * demodulation (index 2).  dfk_profile_read synchronises and returns the summed milliseconds and the
- * number of timed regions of each class. */
+/* Device-time accounting per kernel class for the roofline report: with profiling on, the entry
+ * points record CUDA event pairs on the launching stream around the demodulation launch (index 0),
+ * around the LM launches (index 1), on the side stream around the cold seed fits that overlap the
+ * demodulation (index 2), and around the EKF kernel (index 3).  dfk_profile_read synchronises and
+ * returns the summed milliseconds and the number of timed regions of each class. */
 int dfk_profile_enable(dfk_ctx* ctx, int32_t on);
-int dfk_profile_read(dfk_ctx* ctx, double ms_total[3], int64_t launches[3], int32_t reset);
+int dfk_profile_read(dfk_ctx* ctx, double ms_total[DFK_PROFILE_KINDS], int64_t launches[DFK_PROFILE_KINDS],
+                     int32_t reset);
 /* Measured fp64 FMA throughput of the device in TFLOP/s (8 independent DFMA chains per thread, best of 3):
  * the denominator for the LM kernel's fraction of the FP64 roofline. */
 int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out);
+/* Development overrides of kernel choice and geometry for tuning runs and kernel A/B tests, e.g.
+ * dfk_dev_set("DFK_NO_TILE", 1) (names: csrc/dfk_b200.cu).  Process-wide, set only by these calls -- the library
+ * never reads the environment.  dfk_dev_clear() drops them all. */
+int dfk_dev_set(const char* name, int32_t value);
+void dfk_dev_clear(void);
 /* Kernel launches issued through this context since creation (bench.py's gpu_launches). */
 int64_t dfk_launch_count(dfk_ctx* ctx);
 /* Which demod path the given geometry selects: 1 = a folded TMA kernel (fold / tile / single-period),

@@ -88,13 +88,13 @@ void hh_fit(int N, const double* qi, const double* p0, const double* opts, doubl
 void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, const double* x0,
             const double* p0_diag, const double* q_diag, double r_val, double* rows) {
     EkfState s;
-    for (int i = 0; i < 5; ++i) {
-        s.x[i] = x0[i];
-        for (int j = 0; j < 5; ++j) s.P[i][j] = (i == j) ? p0_diag[i] : 0.0;
-    }
+    for (int i = 0; i < 5; ++i) s.x[i] = x0[i];
+    for (int i = 0; i < 15; ++i) s.P[i] = 0.0;
+    for (int i = 0; i < 5; ++i) s.P[tri(i, i)] = p0_diag[i];
     EkfConsts c;
     c.w_m = 2 * kPi * f_mod;
     c.f_samp = f_samp;
+    c.inv_fs = 1.0 / f_samp;
     for (int i = 0; i < 5; ++i) c.q[i] = q_diag[i];
     c.r = r_val;
     const int64_t nbuf = T / R;
@@ -105,6 +105,24 @@ void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, 
             if (idx < nbuf) std::memcpy(rows + idx * 5, s.x, 5 * sizeof(double));
         }
     }
+}
+
+// sincos_cw on n arguments: out[2i] = sin, out[2i+1] = cos.
+void hh_sincos_cw(const double* x, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) sincos_cw(x[i], out + 2 * i, out + 2 * i + 1);
+}
+
+// Number of sample indices k in [k0, k1) for which sample_time(k) differs from the IEEE quotient k / f_samp.
+int64_t hh_sample_time_mismatches(double f_samp, int64_t k0, int64_t k1) {
+    EkfConsts c;
+    c.f_samp = f_samp;
+    c.inv_fs = 1.0 / f_samp;
+    int64_t bad = 0;
+    for (int64_t k = k0; k < k1; ++k) {
+        volatile double ref = static_cast<double>(k) / f_samp;
+        if (sample_time(static_cast<double>(k), c) != ref) ++bad;
+    }
+    return bad;
 }
 
 // Demod plan (host logic shared with the CUDA launcher) and a scalar emulation of the folded

@@ -39,7 +39,7 @@ def test_header_symbols_exported_and_bound(lib):
 def test_struct_layouts_match_header(lib):
     from deepfmkit_b200 import _lib
     assert ctypes.sizeof(_lib.LmOpts) == 8 + 8 * 8
-    assert ctypes.sizeof(_lib.EkfOpts) == 15 * 8
+    assert ctypes.sizeof(_lib.EkfOpts) == 16 * 8
     assert ctypes.sizeof(_lib.LmCounters) == 5 * 8
     o = _lib.default_lm_opts()
     assert (o.max_lma_steps, o.conv_improve, o.conv_param, o.fitok_threshold) == (100, 1e-9, 1e-9, 1e-3)
@@ -47,7 +47,7 @@ def test_struct_layouts_match_header(lib):
     assert (o.bessel_amp_threshold, o.sincos_amp_threshold) == (0.05, 0.1)
     e = _lib.default_ekf_opts()
     assert list(e.init) == [1.6, 6.0, 0.0, 0.0] and list(e.p0_diag) == [1.0] * 5
-    assert list(e.q_diag) == [1e-8, 1e-8, 1e-6, 1e-6, 1e-8] and np.isnan(e.r_val)
+    assert list(e.q_diag) == [1e-8, 1e-8, 1e-6, 1e-6, 1e-8] and np.isnan(e.r_val) and np.isnan(e.init_dc)
 
 
 def test_no_gpu_means_loud_failure(lib):

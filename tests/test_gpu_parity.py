@@ -107,15 +107,15 @@ def test_demod_vs_oracle_general(torch_mod, ctx, f_samp, f_mod, n, nh):
 
 @pytest.mark.parametrize("name", ["cfg1_quickstart", "fallback_m16"])
 def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
-    """Short periods take the barrier-free tile kernel; DFK_NO_TILE routes the same data through the CTA-per-buffer
-    fold kernel.  Both must sit at the reference's rounding floor."""
+    """Short periods take the barrier-free tile kernel; the DFK_NO_TILE override (an explicit library call, not an
+    environment variable) routes the same data through the CTA-per-buffer fold kernel.  Both must sit at the reference's rounding floor."""
     g, x, f_samp, f_mod, n, nh, R, w0 = _case(golden, name)
     x = np.tile(x[: (len(x) // R) * R], 40)  # enough buffers for every warp of several CTAs, ragged last group
     x = x[: (len(x) // R - 3) * R]
     qi_tile, dc_tile = gpu_demod(torch_mod, ctx, x, R, nh, w0)
-    monkeypatch.setenv("DFK_NO_TILE", "1")
-    qi_fold, dc_fold = gpu_demod(torch_mod, ctx, x, R, nh, w0)
-    monkeypatch.delenv("DFK_NO_TILE")
+    from deepfmkit_b200 import _lib
+    with _lib.dev_overrides(DFK_NO_TILE=1):
+        qi_fold, dc_fold = gpu_demod(torch_mod, ctx, x, R, nh, w0)
     nb = len(g["qi"])
     ref = np.tile(g["qi"], (40, 1))[: len(qi_tile)]
     scale = np.abs(ref).max(axis=1, keepdims=True)

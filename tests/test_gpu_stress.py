@@ -27,6 +27,7 @@ def test_random_geometries(monkeypatch):
     import torch
     from deepfmkit_b200 import _lib
     ctx = _lib.Context(0)
+    lib = _lib.load_library()
     ctx.use_torch_stream()  # the NaN pre-fills below are torch kernels: same stream, so they are ordered before ours
     rng = np.random.RandomState(31337)
     worst = 0.0
@@ -49,10 +50,9 @@ def test_random_geometries(monkeypatch):
             nbuf = max(1, 40_000_000 // (P * n))
         R = P * n
         w0 = 2.0 * np.pi * 1000.0 / (1000.0 * P)
+        lib.dfk_dev_clear()
         if rng.rand() < 0.3:
-            monkeypatch.setenv("DFK_TILE_NSTAGES", str(int(rng.randint(2, 6))))
-        else:
-            monkeypatch.delenv("DFK_TILE_NSTAGES", raising=False)
+            lib.dfk_dev_set(b"DFK_TILE_NSTAGES", int(rng.randint(2, 6)))
         t = np.arange(nbuf * R)
         x = 1.0 + np.cos(0.3 + 4.0 * np.cos(2 * np.pi * t / P + 0.1)) + 0.05 * rng.randn(nbuf * R)
         ref_qi, ref_dc = numpy_lockin(x, R, nh, w0)
@@ -68,6 +68,7 @@ def test_random_geometries(monkeypatch):
             assert np.max(np.abs(dc.cpu().numpy() - ref_dc)) <= 1e-13, (trial, kind, P, n, nh, nbuf, rep)
             worst = max(worst, err)
         cases += 1
+    lib.dfk_dev_clear()
     ctx.close()
     assert cases == 70 and worst <= 1e-12
 

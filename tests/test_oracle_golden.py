@@ -118,3 +118,72 @@ def test_ekf_full_record_bit_exact(golden, name):
 def test_crlb_helper_is_finite():
     s = orc.crlb_sigma_m(6.0, 10, 40.0, 4000)
     assert 1e-5 < s < 1e-2
+
+
+# ---- full-size fixtures (tests/golden/make_golden_full.py) -------------------------------------------------------
+def _full_signal(g):
+    m, f_samp, f_mod, secs, snr, trial, phi, psi = g["meta"][:8]
+    x = orc.snr_signal(m, f_samp, f_mod, secs, snr, seed=int(trial), phi0=phi, psi0=psi)
+    assert np.array_equal(x[:16], g["x_head"]) and np.array_equal(x[-16:], g["x_tail"])
+    assert x.sum() == g["x_sum"][0] and np.abs(x).sum() == g["x_sum"][1]
+    return x
+
+
+def test_full_cfg1_all_500_buffers_bit_exact(golden):
+    g = golden("full_cfg1")
+    x = _full_signal(g)
+    assert np.array_equal(orc.nls_fit(x, 200e3, 1000.0, 20, 10, schedule="sequential"), g["rows_seq"])
+    assert np.array_equal(orc.nls_fit(x, 200e3, 1000.0, 20, 10, schedule="seeded", n_chunks=int(g["meta"][10])),
+                          g["rows_par"])
+    assert len(g["rows_seq"]) == 500
+
+
+@pytest.mark.parametrize("name", ["full_cfg2_first", "full_cfg2_last", "full_cfg3_c37"])
+def test_full_slab_prefix_bit_exact(golden, name):
+    """A prefix of the sequential chain is the chain of the prefix: pin the first 40 buffers of the long fixtures."""
+    g = golden(name)
+    x = _full_signal(g)
+    f_samp, n, nh = g["meta"][1], int(g["meta"][8]), int(g["meta"][9])
+    R = int(f_samp / 1000.0 * n)
+    rows = orc.nls_fit(x[: 40 * R], f_samp, 1000.0, n, nh, schedule="sequential")
+    assert np.array_equal(rows, g["rows_seq"][:40])
+    w0 = orc.rad_per_sample(f_samp, 1000.0)
+    for b in (0, 39, len(g["qi"]) - 1):
+        assert np.array_equal(orc.lockin_means(x[b * R:(b + 1) * R], w0, nh), g["qi"][b])
+
+
+def test_full_cfg5_subset_bit_exact(golden):
+    g = golden("full_cfg5")
+    assert g["rows"].shape == (19, 1000, 7)
+    for a, m in enumerate(g["ms"]):
+        for t in (0, 1, 499, 999):
+            x = orc.snr_signal(float(m), 200e3, 1000.0, 1e-3, 40.0, seed=t)
+            assert np.array_equal(orc.nls_fit(x, 200e3, 1000.0, 1, 15, init_m=float(m))[0], g["rows"][a, t])
+
+
+@pytest.mark.parametrize("name", ["drift_phi_1um", "drift_phi_slow"])
+def test_drifting_records_bit_exact(golden, name):
+    """'asd'-mode physics restated by the oracle (bit-equal record) and all three reference schedules on it."""
+    g = golden(name)
+    m, fs, fm, secs, trial, amp_n, aamp, af = g["meta"]
+    x, truth = orc.asd_signal(m, fs, fm, secs, trial=int(trial), amp_n=amp_n, arml_mod_amp=aamp, arml_mod_f=af)
+    assert np.array_equal(x[:16], g["x_head"]) and np.array_equal(x[-16:], g["x_tail"])
+    assert x.sum() == g["x_sum"][0] and np.abs(x).sum() == g["x_sum"][1]
+    assert np.array_equal(truth[::4000], g["phi_sim"])
+    assert np.array_equal(orc.nls_fit(x, fs, fm, 20, 10, schedule="sequential"), g["rows_seq"])
+    assert np.array_equal(orc.nls_fit(x, fs, fm, 20, 10, schedule="seeded", n_chunks=3), g["rows_par3"])
+    assert np.array_equal(orc.nls_fit(x, fs, fm, 20, 10, schedule="seeded", n_chunks=8), g["rows_par8"])
+    # the schedule is observable on these records: seeding every buffer from buffer 0 changes flags
+    each = orc.nls_fit(x, fs, fm, 20, 10, schedule="gpu")
+    assert not np.array_equal(each[:, 6], g["rows_seq"][:, 6])
+
+
+def test_full_ekf_channel_prefix_bit_exact(golden):
+    """The oracle's loop against EKFFitter.fit on the first 0.25 s (50 000 steps) of a cfg-4 channel.  The filter's
+    initial dc and R are whole-record moments, so the prefix is run with those of the full second."""
+    g = golden("full_ekf_8ch")
+    c = g["channels"][3]
+    z = orc.snr_signal(6.0, 200e3, 1000.0, 1.0, 40.0, seed=int(c), phi0=2 * np.pi * c / 4096)
+    assert np.array_equal(z[:16], g["x_head"][3])
+    rows = orc.ekf_track(z[:48_000], 200e3, 1000.0, 20, r_val=np.var(z), init_dc=np.mean(z))
+    assert np.array_equal(rows[:, :5], g["rows"][3][:12, :5])
