@@ -158,6 +158,16 @@ def main():
         elif c == "cfg4late":
             ekf_case(ctx, "cfg4late", 4096, 0.25, 1, False, note="slab starting at t = 90 s", start_s=90.0)
             ekf_case(ctx, "cfg4late", 4096, 0.25, 1, False, note="slab starting at t = 0 s", start_s=0.0)
+        elif c == "cfg4cpw":  # channels per warp: does a one-warp block get a scheduler of its own?
+            for cpw in (4, 8, 16, 32):
+                _lib.load_library().dfk_dev_set(b"DFK_EKF_CPW", cpw)
+                ekf_case(ctx, f"cfg4 cpw={cpw}", 4096, 0.25, 2, False)
+            _lib.load_library().dfk_dev_clear()
+        elif c == "cfg4unroll":
+            for u in (1, 2, 4):
+                _lib.load_library().dfk_dev_set(b"DFK_EKF_UNROLL", u)
+                ekf_case(ctx, f"cfg4 unroll={u}", 4096, 0.25, 2, False)
+            _lib.load_library().dfk_dev_clear()
         elif c == "cfg4small":
             ekf_case(ctx, "cfg4small", 4096, 0.1, 1, False)
             ekf_case(ctx, "cfg4small", 4096, 0.1, 1, True)

@@ -62,7 +62,7 @@ struct dfk_ctx {
     static constexpr size_t kStageBytes = 64u << 20;
     void* stager[kStagers] = {nullptr, nullptr, nullptr};
     cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
-    DevBuf qi, dc, retry, counters, slab[2], rows, stats, misc, qi_seed, dc_seed;
+    DevBuf qi, dc, retry, counters, slab[2], rows, stats, stats_part, misc, qi_seed, dc_seed;
     int64_t launches = 0;
     bool stats_ready = false;      // ctx->stats already holds whole-record moments (streamed EKF)
     size_t host_slab_bytes = 0;    // 0 = defaults; else the slab size of the host-pointer entries (tests force streaming)
@@ -760,6 +760,31 @@ Schedule schedule_of(int32_t seeded) {
     return sc;
 }
 
+// Per-channel mean and variance of a device record (either layout); see dfk_ekf_kernels.cuh.
+int launch_channel_stats(dfk_ctx* ctx, const double* z, int64_t T, int64_t C, int64_t ld_t, int64_t ld_c, double* stats,
+                         double* acc, cudaStream_t st) {
+    if (ld_c == 1 && C > 1) {  // time-major: coalesced rows, time split over warps and blocks
+        const int64_t groups = (C + 31) / 32;
+        int nsplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(64, (4ll * ctx->sm_count) / groups)));
+        nsplit = static_cast<int>(std::min<int64_t>(nsplit, std::max<int64_t>(1, T / 256)));
+        int rc = ensure(ctx, ctx->stats_part, static_cast<size_t>(2) * nsplit * C * sizeof(double));
+        if (rc) return rc;
+        double* sums = static_cast<double*>(ctx->stats_part.ptr);
+        double* sq = sums + static_cast<size_t>(nsplit) * C;
+        const dim3 grid(static_cast<unsigned>(groups), static_cast<unsigned>(nsplit));
+        dfk::stats_tm_kernel<<<grid, dfk::kStatsThreads, 0, st>>>(z, T, C, ld_t, 0, nullptr, 0, sums);
+        dfk::stats_tm_kernel<<<grid, dfk::kStatsThreads, 0, st>>>(z, T, C, ld_t, 1, sums, nsplit, sq);
+        dfk::stats_tm_finish_kernel<<<static_cast<int>((C + 127) / 128), 128, 0, st>>>(sums, sq, nsplit, T, C, stats, acc);
+        ctx->launches += 3;
+    } else {
+        const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
+        dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z, T, C, ld_t, ld_c, stats, acc);
+        ctx->launches++;
+    }
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -854,7 +879,7 @@ int dfk_destroy(dfk_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     DevBuf* bufs[] = {&ctx->qi, &ctx->dc, &ctx->retry, &ctx->counters, &ctx->slab[0], &ctx->slab[1],
-                      &ctx->rows, &ctx->stats, &ctx->misc, &ctx->qi_seed, &ctx->dc_seed};
+                      &ctx->rows, &ctx->stats, &ctx->stats_part, &ctx->misc, &ctx->qi_seed, &ctx->dc_seed};
     for (DevBuf* b : bufs)
         if (b->ptr) cudaFree(b->ptr);
     for (auto& kind : ctx->prof_ev)
@@ -1071,10 +1096,8 @@ int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, 
     if (k0 == 0 && need_stats && !ctx->stats_ready) {
         // initial dc and default measurement variance come from the first (or only) slab, unless the caller
         // prepared whole-record moments (dfk_ekf_host on a streamed record)
-        const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
-        dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(z_dev, T, C, ld_t, ld_c, stats, nullptr);
-        ctx->launches++;
-        DFK_CUDA(cudaGetLastError());
+        rc = launch_channel_stats(ctx, z_dev, T, C, ld_t, ld_c, stats, nullptr, st);
+        if (rc) return rc;
     }
     dfk::EkfLaunch a;
     a.k0 = k0;
@@ -1092,11 +1115,17 @@ int dfk_ekf_stream_dev(dfk_ctx* ctx, const double* z_dev, int64_t T, int64_t C, 
     const int64_t schedulers = static_cast<int64_t>(ctx->sm_count) * 4;
     int cpw = 1;
     while (cpw < 32 && (C + cpw - 1) / cpw > schedulers) cpw <<= 1;
+    const int forced = dev_int("DFK_EKF_CPW", 0);
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) cpw = forced;
     a.cpw = cpw;
     const int64_t grid = (C + cpw - 1) / cpw;
     if (grid > std::numeric_limits<int>::max()) return fail(DFK_ERR_ARG, "too many channels");
     ProfScope ps(ctx, 3, st);
-    dfk::ekf_kernel<<<static_cast<int>(grid), 32, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev);
+    switch (dev_int("DFK_EKF_UNROLL", 1)) {
+        case 2: dfk::ekf_kernel<2><<<static_cast<int>(grid), 32, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev); break;
+        case 4: dfk::ekf_kernel<4><<<static_cast<int>(grid), 32, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev); break;
+        default: dfk::ekf_kernel<1><<<static_cast<int>(grid), 32, 0, st>>>(z_dev, T, C, ld_t, ld_c, R, a, stats, rows_dev); break;
+    }
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
@@ -1158,7 +1187,6 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
         if (rc) return rc;
         slab_rows = static_cast<double*>(ctx->qi.ptr);
         const bool need_stats = std::isnan(opts->init_dc) || std::isnan(opts->r_val);
-        const int sgrid = static_cast<int>(std::min<int64_t>(C, static_cast<int64_t>(ctx->sm_count) * 8));
         int64_t slab_no = 0;
         for (int pass = need_stats ? 0 : 1; pass < 2; ++pass) {
             if (pass == 0) DFK_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(C) * 3 * 8, st));
@@ -1176,9 +1204,8 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
                 DFK_CUDA(cudaEventRecord(ctx->copied[sl], ctx->copy_stream));
                 DFK_CUDA(cudaStreamWaitEvent(st, ctx->copied[sl], 0));
                 if (pass == 0) {
-                    dfk::channel_stats_kernel<<<sgrid, dfk::kStatsThreads, 0, st>>>(dst, tn, C, 1, tn, nullptr, acc);
-                    ctx->launches++;
-                    DFK_CUDA(cudaGetLastError());
+                    rc = launch_channel_stats(ctx, dst, tn, C, 1, tn, nullptr, acc, st);
+                    if (rc) return rc;
                 } else {
                     const int64_t nb = tn / R;
                     ctx->stats_ready = need_stats;

@@ -113,7 +113,13 @@ __global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __res
         }
         if (live && rank == 0) {
             double* row = rows + u * map.row_mul * kRowStride;
-            const bool done = ssq < o.fitok_threshold;
+            const bool converged = ssq < o.fitok_threshold;
+            // Chain schedule: a descent that converged with a < 0 or m < 0 took a detour the chain, starting next to
+            // the solution, does not take -- and the reference's sign normalisation (fit.py:352-357) is not a symmetry
+            // of the model (the exact one is (a, -m, phi) = (a, m, -phi)), so the two would report different phi.
+            // Such fits are parked too (flag 2) and refitted from their predecessor.
+            const bool flipped = parked_flags && (p[0] < 0.0 || p[1] < 0.0);
+            const bool done = converged && !flipped;
             if (done) normalise_params(p);
             row[0] = p[0]; row[1] = p[1]; row[2] = p[2]; row[3] = p[3];
             row[4] = dc ? dc[u] : 0.0;
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(TPB, MINB) lm_first_kernel(const double* __res
             row[6] = done ? 0.0 : -1.0;  // -1: parked for the retry stage
             row[7] = static_cast<double>(steps);
             if (parked_flags) {  // chain schedule: lm_chain_kernel walks the parked runs
-                parked_flags[u] = done ? 0 : 1;
+                parked_flags[u] = done ? 0 : (converged ? 2 : 1);
             } else if (!done) {
                 retry_list[atomicAdd(retry_count, 1)] = static_cast<int>(u);
             }
@@ -171,11 +177,12 @@ __global__ void __launch_bounds__(kLmThreads) lm_chain_kernel(const double* __re
                 double ssq;
                 int steps, status;
                 __syncwarp();
-                if (start) {  // first descent from the chunk seed was stage 1: continue with the fallback
+                if (start) {  // the first descent from the chunk seed was stage 1, the reference's own start
                     p[0] = row[0]; p[1] = row[1]; p[2] = row[2]; p[3] = row[3];
                     ssq = row[5];
                     steps = static_cast<int>(row[7]);
-                    status = retry_fit<32>(N, q, 1, bes, kLmThreads, o, p, ssq, steps, cnt);
+                    // flag 2: it converged (with a sign to normalise); flag 1: continue with the fallback
+                    status = parked[v] == 2 ? 0 : retry_fit<32>(N, q, 1, bes, kLmThreads, o, p, ssq, steps, cnt);
                     normalise_params(p);
                 } else {
                     if (!have_prev) {

@@ -91,6 +91,7 @@ void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, 
     for (int i = 0; i < 5; ++i) s.x[i] = x0[i];
     for (int i = 0; i < 15; ++i) s.P[i] = 0.0;
     for (int i = 0; i < 5; ++i) s.P[tri(i, i)] = p0_diag[i];
+    for (int i = 0; i < 5; ++i) s.kp[i] = s.hp[i] = 0.0;
     EkfConsts c;
     c.w_m = 2 * kPi * f_mod;
     c.f_samp = f_samp;
@@ -99,7 +100,7 @@ void hh_ekf(const double* z, int64_t T, int64_t R, double f_samp, double f_mod, 
     c.r = r_val;
     const int64_t nbuf = T / R;
     for (int64_t k = 0; k < T; ++k) {
-        ekf_step(s, z[k], static_cast<double>(k), c);
+        ekf_step<false>(s, z[k], carrier_angle(static_cast<double>(k), c), c);
         if ((k + 1) % R == 0) {
             const int64_t idx = (k + 1) / R - 1;
             if (idx < nbuf) std::memcpy(rows + idx * 5, s.x, 5 * sizeof(double));

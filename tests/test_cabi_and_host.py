@@ -184,16 +184,25 @@ def test_sharded_gather_world_size_2_gloo(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """bench.py's CPU pieces: the sample generator and the pool schedule agree with the sequential oracle."""
+    """bench.py's CPU arm: the port's pool schedule agrees with the sequential oracle, and the arm that times the
+    reference itself (baseline/_ref, when installed) returns the same rows as the port on the same sample."""
     sys.path.insert(0, ROOT)
     import bench
     from oracle import dfmi_oracle as orc
-    x = bench.cpu_sample(6, seed=1)
+    x = orc.snr_signal(bench.M_TRUE, bench.F_SAMP, bench.F_MOD, 6 * bench.R / bench.F_SAMP, bench.SNR_DB, seed=1)
     assert len(x) == 6 * bench.R
     rows = orc.nls_fit_pool(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, n_procs=2)
     ref = orc.nls_fit(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, schedule="seeded", n_chunks=2)
     assert np.array_equal(rows, ref)
     assert bench.NBUF == 180000 and bench.R == 20000
+    arm = bench.cpu_arm()
+    assert arm.kind in ("reference", "port")
+    if arm.kind == "reference":
+        df = arm.rfitters.StandardNLSFitter({"n": bench.N_CYCLES, "ndata": bench.NDATA}).fit(
+            arm._raw(x, bench.F_SAMP, bench.F_MOD), parallel=True, n_cores=2)
+        got = df[["amp", "m", "phi", "psi", "dc", "ssq", "fitok"]].to_numpy(dtype=float)
+        assert np.array_equal(got, ref)
+    assert arm.nls_pool(x, bench.F_SAMP, bench.F_MOD, bench.N_CYCLES, bench.NDATA, 2) > 0
 
 
 def test_reference_facade_dispatches_to_b200_fitters(lib, tmp_path):
@@ -262,5 +271,5 @@ def test_bench_reference_arm_emits_the_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["dtype"] == "f64" and d["vs_baseline"] is None and d["value"] > 0
     assert d["config"]["workload"].startswith("cfg2") and "model" not in d["config"]
-    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -314,9 +314,10 @@ def test_ekf_batch_layouts_agree(torch_mod, golden):
     z = np.stack([x, x[::-1].copy(), x * 1.01])
     a = ekf_fit_batch(z, 200e3, 1000.0, 20)
     b = ekf_fit_batch(np.ascontiguousarray(z.T), 200e3, 1000.0, 20, time_major=True)
-    assert np.array_equal(a, b)
+    # the time-major record sums its mean / variance in a different order: equal to rounding, not to the bit
+    assert np.max(np.abs(a - b)) <= 1e-12
     ref = orc.ekf_track(x, 200e3, 1000.0, 20)
-    assert np.max(np.abs(a[0, :, :5] - ref[:, :5])) < 1e-9
+    assert np.max(np.abs(a[0, :, :5] - ref[:, :5])) < 1e-11
 
 
 def _ekf_case(args):
