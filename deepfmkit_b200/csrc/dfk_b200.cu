@@ -475,18 +475,29 @@ int launch_first_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map
     return DFK_OK;
 }
 
-int launch_flat(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
-                const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+template <int MINB>
+int launch_flat_b(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
+                  const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(N + 2 + dfk::kNeDoubles) * dfk::kLmThreads * sizeof(double);
-    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_flat_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DFK_CUDA(cudaFuncSetAttribute(dfk::lm_flat_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     const int64_t blocks = (nfit + dfk::kLmThreads - 1) / dfk::kLmThreads;
-    const int per_sm = dev_int("DFK_LM_FLAT_BLOCKS", 4);
+    const int per_sm = dev_int("DFK_LM_FLAT_BLOCKS", MINB);
     const int grid = static_cast<int>(std::min<int64_t>(blocks, static_cast<int64_t>(ctx->sm_count) * per_sm));
-    dfk::lm_flat_kernel<4><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
+    dfk::lm_flat_kernel<MINB><<<grid, dfk::kLmThreads, smem, st>>>(qi, nfit, map, N, gs, dc, o, rows, list, count, counters);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
+}
+
+int launch_flat(dfk_ctx* ctx, const double* qi, int64_t nfit, dfk::FitMap map, int N, const dfk::GuessSrc& gs, const double* dc,
+                const dfk::LmOpts& o, double* rows, int* list, int* count, dfk::LmCounts* counters, cudaStream_t st) {
+    switch (dev_int("DFK_LM_FLAT_MINB", 4)) {
+        case 5: return launch_flat_b<5>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 6: return launch_flat_b<6>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        case 8: return launch_flat_b<8>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+        default: return launch_flat_b<4>(ctx, qi, nfit, map, N, gs, dc, o, rows, list, count, counters, st);
+    }
 }
 
 template <int G>
@@ -1248,7 +1259,7 @@ int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, in
                            double psi0, double snr_db, uint64_t seed) {
     DFK_ENTER(ctx);
     if (T < 0 || C < 0) return fail(DFK_ERR_ARG, "bad geometry");
-    if (t0 < 0 || (t0 & 1)) return fail(DFK_ERR_ARG, "t0 must be even and non-negative");
+    if (t0 < 0) return fail(DFK_ERR_ARG, "t0 must be non-negative");
     if (ld_c < T) return fail(DFK_ERR_ARG, "channel stride shorter than the slab");
     if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
     if (T == 0 || C == 0) return DFK_OK;
@@ -1270,9 +1281,24 @@ int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, in
     p.psi0 = psi0;
     p.sigma_scale = std::pow(10.0, -snr_db / 20.0);
     p.seed = seed;
-    const int64_t pairs = ((T + 1) / 2) * C;
-    const int grid = static_cast<int>(std::min<int64_t>((pairs + 255) / 256, static_cast<int64_t>(ctx->sm_count) * 32));
-    dfk::synth_snr_kernel<<<grid, 256, 0, ctx->stream()>>>(p);
+    // one tabulated clean period per block when the period is a whole number of samples and the table pays for
+    // itself: all channels share it (dphi == 0), or every channel's slab is several periods long
+    const bool shared_tab = dphi == 0.0 || C == 1;
+    const int table = (p.P > 0 && p.P <= dfk::kSynthMaxTable && (shared_tab || T >= 8 * p.P)) ? 1 : 0;
+    const int64_t nq = ((t0 + T + 3) >> 2) - (t0 >> 2);
+    int64_t ch_per_block = 1;
+    if (shared_tab || !table) {  // short records: several channels per block so that a block has ~64k samples
+        ch_per_block = std::max<int64_t>(1, std::min<int64_t>(C, 65536 / std::max<int64_t>(T, 1)));
+    }
+    const int64_t gy = (C + ch_per_block - 1) / ch_per_block;
+    int64_t gx = std::max<int64_t>(1, std::min<int64_t>((nq + dfk::kSynthThreads - 1) / dfk::kSynthThreads,
+                                                       (static_cast<int64_t>(ctx->sm_count) * 16 + gy - 1) / gy));
+    if (gy > 65535) {  // grid.y limit: fold the excess into more channels per block
+        ch_per_block = (C + 65534) / 65535;
+    }
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((C + ch_per_block - 1) / ch_per_block));
+    const size_t smem = table ? static_cast<size_t>(p.P) * sizeof(double) : 0;
+    dfk::synth_snr_kernel<<<grid, dfk::kSynthThreads, smem, ctx->stream()>>>(p, table, ch_per_block);
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;

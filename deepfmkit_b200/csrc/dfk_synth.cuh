@@ -1,7 +1,7 @@
 // 'snr'-mode synthetic DFMI records generated in HBM (physics.py:475-530 restated for the device):
 //   y[t] = A (1 + C cos(phi0 + m cos(2 pi f_mod t / f_samp + psi0))) + sigma * N(0, 1).
 // The noise comes from a counter-based generator (Philox4x32-10 + Box-Muller), so a record is a pure
-// function of (seed, channel, t): any slab can be generated on any GPU.  It is statistically, not
+// function of (seed, channel, t): any slab, starting at any sample, can be generated on any GPU.  It is statistically, not
 // bitwise, equivalent to the reference's MT19937 stream; parity tests use reference-generated input.
 #pragma once
 #include "dfk_common.cuh"
@@ -24,7 +24,7 @@ DFK_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 struct SynthParams {
     double* x;
     long long T, C;
-    long long t0;    // absolute index of the first sample generated (even); the stream is a function of absolute t
+    long long t0;    // absolute index of the first sample generated; the stream is a function of absolute t
     long long ld_c;  // output samples between consecutive channels
     long long P;  // samples per modulation period when it is a whole number, else 0
     double f_ratio;  // f_mod / f_samp
@@ -42,43 +42,107 @@ DFK_D double clean_ac_rms(double amp, double vis, double phi, double m) {
     return amp * vis * sqrt(fmax(var, 0.0));
 }
 
-__global__ void __launch_bounds__(256) synth_snr_kernel(const SynthParams p) {
-    const long long pairs_per_ch = (p.T + 1) / 2;
-    const long long total = pairs_per_ch * p.C;
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256ll) {
-        const long long c = i / pairs_per_ch;
-        const long long tl = (i - c * pairs_per_ch) * 2;  // index inside the slab
-        const long long t0 = p.t0 + tl;                  // absolute sample index
-        const double phi = p.phi0 + static_cast<double>(c) * p.dphi;
-        const double sigma = clean_ac_rms(p.amp, p.vis, phi, p.m) * p.sigma_scale;
-        uint32_t r[4];
-        const unsigned long long key = p.seed + static_cast<unsigned long long>(c);
-        philox4x32_10(static_cast<uint32_t>(t0), static_cast<uint32_t>(t0 >> 32), 0x5eedu, 0u,
-                      static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), r);
-        // two 53-bit uniforms in (0, 1]
-        const double u1 = (static_cast<double>((static_cast<unsigned long long>(r[0]) << 21) ^ (r[1] >> 11)) + 1.0) *
-                          (1.0 / 9007199254740992.0);
-        const double u2 = static_cast<double>((static_cast<unsigned long long>(r[2]) << 21) ^ (r[3] >> 11)) *
-                          (1.0 / 9007199254740992.0);
-        const double rad = sqrt(-2.0 * log(u1));
-        double sn, cn;
-        sincospi(2.0 * u2, &sn, &cn);
-        const double g[2] = {rad * cn, rad * sn};
+// Sample t of channel c:  clean_c[t] + sigma_c * z(seed + c, t).
+//   * The noise uses one Philox4x32-10 block per four consecutive samples (counter = absolute t / 4, key = seed + c):
+//     four 32-bit uniforms -> two Box-Muller pairs evaluated in fp32 (the noise is 20..60 dB below the signal, so its
+//     own 2^-24 granularity is 7 digits below anything a fit can see; |z| <= 6.66).  fp64 log / sqrt / sincospi per
+//     pair is what made the first generator compute-bound at 0.48 TB/s.
+//   * The clean signal is periodic with P = f_samp / f_mod samples whenever that is a whole number: a block tabulates
+//     one period of its channel in shared memory (cospi + cos in fp64, P evaluations) and reads it back by t mod P.
+//     table == 0 (incommensurate or very long period, or records so short that a table per channel would cost more
+//     than it saves) evaluates the two cosines per sample as before.
+// Blocks: blockIdx.y = channel (or channel group when all channels share phi), blockIdx.x strides the quads.
+constexpr int kSynthThreads = 256;
+constexpr int kSynthMaxTable = 4096;  // doubles
+
+DFK_D double synth_clean(const SynthParams& p, double phi, long long t) {
+    double frac;
+    if (p.P > 0) {
+        frac = static_cast<double>(t % p.P) / static_cast<double>(p.P);
+    } else {
+        const double ph = static_cast<double>(t) * p.f_ratio;
+        frac = ph - floor(ph);
+    }
+    const double th = cospi(2.0 * frac + p.psi0 * (1.0 / kPi));
+    return p.amp * (1.0 + p.vis * cos(phi + p.m * th));
+}
+
+DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
+                      long long q) {
+    const unsigned long long key = p.seed + static_cast<unsigned long long>(c);
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), 0x5eedu, 0u, static_cast<uint32_t>(key),
+                  static_cast<uint32_t>(key >> 32), r);
+    float z[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const long long t = t0 + e;
-            if (tl + e >= p.T) break;
-            double frac;
-            if (p.P > 0) {
-                frac = static_cast<double>(t % p.P) / static_cast<double>(p.P);
-            } else {
-                const double ph = static_cast<double>(t) * p.f_ratio;
-                frac = ph - floor(ph);
-            }
-            const double th = cospi(2.0 * frac + p.psi0 * (1.0 / kPi));
-            const double clean = p.amp * (1.0 + p.vis * cos(phi + p.m * th));
-            p.x[c * p.ld_c + tl + e] = fma(sigma, g[e], clean);
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = (static_cast<float>(r[2 * h]) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+        const float u2 = static_cast<float>(r[2 * h + 1]) * 2.3283064365386963e-10f;       // [0, 1]
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cn;
+        sincospif(2.0f * u2, &sn, &cn);
+        z[2 * h] = rad * cn;
+        z[2 * h + 1] = rad * sn;
+    }
+    const long long t4 = q << 2;
+    double y[4];
+    int jm = table ? static_cast<int>(t4 % p.P) : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        double clean;
+        if (table) {
+            clean = clean_tab[jm];
+            if (++jm == p.P) jm = 0;
+        } else {
+            clean = synth_clean(p, phi, t4 + e);
         }
+        y[e] = fma(sigma, static_cast<double>(z[e]), clean);
+    }
+    double* dst = p.x + c * p.ld_c - p.t0 + t4;  // indexed by absolute t
+    if (t4 >= p.t0 && t4 + 4 <= p.t0 + p.T && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        reinterpret_cast<double2*>(dst)[0] = make_double2(y[0], y[1]);
+        reinterpret_cast<double2*>(dst)[1] = make_double2(y[2], y[3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (t4 + e >= p.t0 && t4 + e < p.t0 + p.T) dst[e] = y[e];
+    }
+}
+
+__global__ void __launch_bounds__(kSynthThreads) synth_snr_kernel(const SynthParams p, int table, long long ch_per_block) {
+    extern __shared__ double clean_tab[];
+    __shared__ double sigma_sh;
+    const long long q_first = p.t0 >> 2;  // first and one-past-last Philox block of the slab
+    const long long q_end = (p.t0 + p.T + 3) >> 2;
+    const long long nq = q_end - q_first;
+    const long long c_lo = blockIdx.y * ch_per_block;
+    const long long c_hi = (c_lo + ch_per_block < p.C) ? c_lo + ch_per_block : p.C;
+    const long long stride = static_cast<long long>(gridDim.x) * kSynthThreads;
+    const long long first = blockIdx.x * static_cast<long long>(kSynthThreads) + threadIdx.x;
+    auto prepare = [&](double phi) {  // clean period and noise scale of a channel phase, once per block
+        __syncthreads();
+        if (threadIdx.x == 0) sigma_sh = clean_ac_rms(p.amp, p.vis, phi, p.m) * p.sigma_scale;
+        if (table)
+            for (int j = threadIdx.x; j < p.P; j += kSynthThreads) clean_tab[j] = synth_clean(p, phi, j);
+        __syncthreads();
+        return sigma_sh;
+    };
+    if (p.dphi == 0.0 || c_hi - c_lo == 1) {
+        // one phase for the whole block: its (channel, quad) pairs are one flat index space, so that short
+        // records (one period per channel in the Monte-Carlo shape) still fill every thread
+        const double phi = p.phi0 + static_cast<double>(c_lo) * p.dphi;
+        const double sigma = prepare(phi);
+        const long long total = (c_hi - c_lo) * nq;
+        for (long long i = first; i < total; i += stride) {
+            const long long dc = i / nq;
+            synth_quad(p, table, clean_tab, phi, sigma, c_lo + dc, q_first + (i - dc * nq));
+        }
+        return;
+    }
+    for (long long c = c_lo; c < c_hi; ++c) {
+        const double phi = p.phi0 + static_cast<double>(c) * p.dphi;
+        const double sigma = prepare(phi);
+        for (long long i = first; i < nq; i += stride) synth_quad(p, table, clean_tab, phi, sigma, c, q_first + i);
     }
 }
 

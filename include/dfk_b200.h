@@ -171,8 +171,8 @@ int dfk_synth_snr_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, double 
                       double m, double amp, double visibility, double phi0, double dphi, double psi0,
                       double snr_db, uint64_t seed);
 
-/* Samples t0 .. t0+T-1 of the same streams (t0 even), channel c written at x_dev + c * ld_c: any slab of
- * a long record can be produced on its own, on any GPU. */
+/* Samples t0 .. t0+T-1 of the same streams, channel c written at x_dev + c * ld_c: any slab of a long
+ * record can be produced on its own, on any GPU. */
 int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, int64_t ld_c, int64_t t0, double f_samp,
                            double f_mod, double m, double amp, double visibility, double phi0, double dphi,
                            double psi0, double snr_db, uint64_t seed);
