@@ -16,7 +16,7 @@ from ._build import LIB_PATH
 
 ROW_STRIDE = 8
 MAX_HARMONICS = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 PROFILE_KINDS = 4
 SCHED_INDEPENDENT = 0   # every buffer a cold start from init
 SCHED_EACH = -1         # every buffer its own chunk, seeded from buffer 0 (pool schedule at n_cores >= nbuf - 1)
@@ -36,6 +36,12 @@ class LmOpts(ctypes.Structure):
 class EkfOpts(ctypes.Structure):
     _fields_ = [("init", ctypes.c_double * 4), ("p0_diag", ctypes.c_double * 5),
                 ("q_diag", ctypes.c_double * 5), ("r_val", ctypes.c_double), ("init_dc", ctypes.c_double)]
+
+
+class LpsdOpts(ctypes.Structure):
+    _fields_ = [("olap", ctypes.c_double), ("bmin", ctypes.c_double), ("lmin", ctypes.c_int64),
+                ("jdes", ctypes.c_int32), ("kdes", ctypes.c_int32), ("order", ctypes.c_int32),
+                ("window", ctypes.c_int32), ("psll", ctypes.c_double)]
 
 
 class LmCounters(ctypes.Structure):
@@ -75,6 +81,13 @@ SYMBOLS = {
     "dfk_nls_fit_seeded_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
     "dfk_set_host_slab_bytes": (ctypes.c_int, [_vp, _i64]),
+    "dfk_downsample_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "dfk_downsample_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "dfk_default_lpsd_opts": (None, [ctypes.POINTER(LpsdOpts)]),
+    "dfk_lpsd_plan": (ctypes.c_int, [_i64, _d, ctypes.POINTER(LpsdOpts), _i32, ctypes.POINTER(_i32), _vp, _vp, _vp, _vp,
+                                     _vp]),
+    "dfk_lpsd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _d, ctypes.POINTER(LpsdOpts), _i32,
+                                    ctypes.POINTER(_i32), _vp, _vp, _vp, _vp, _vp]),
     "dfk_lm_counters_read": (ctypes.c_int, [_vp, ctypes.POINTER(LmCounters), _i32]),
     "dfk_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "dfk_profile_read": (ctypes.c_int, [_vp, c_double_p, ctypes.POINTER(_i64), _i32]),
@@ -140,6 +153,26 @@ def default_ekf_opts() -> EkfOpts:
     o = EkfOpts()
     load_library().dfk_default_ekf_opts(ctypes.byref(o))
     return o
+
+
+def default_lpsd_opts() -> LpsdOpts:
+    o = LpsdOpts()
+    load_library().dfk_default_lpsd_opts(ctypes.byref(o))
+    return o
+
+
+def lpsd_plan(N, fs, opts=None) -> dict:
+    """Frequency plan of the log-frequency estimate (host only, no GPU needed): f, r, m, L, K arrays."""
+    lib = load_library()
+    opts = opts if opts is not None else default_lpsd_opts()
+    nf = _i32()
+    _check(lib, lib.dfk_lpsd_plan(int(N), float(fs), ctypes.byref(opts), 0, ctypes.byref(nf), None, None, None, None, None))
+    n = int(nf.value)
+    f, r, m = np.empty(n), np.empty(n), np.empty(n)
+    L, K = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    _check(lib, lib.dfk_lpsd_plan(int(N), float(fs), ctypes.byref(opts), n, ctypes.byref(nf), f.ctypes.data, r.ctypes.data,
+                                  m.ctypes.data, L.ctypes.data, K.ctypes.data))
+    return {"f": f, "r": r, "m": m, "L": L, "K": K}
 
 
 def _host_array(a):
@@ -282,6 +315,30 @@ class Context:
         _check(self.lib, self.lib.dfk_ekf_host(self._h, zp, T, C, int(R), float(f_samp), float(f_mod),
                                                ctypes.byref(opts) if opts is not None else None, rows.ctypes.data))
         return rows
+
+    # ---- post-fit step ---------------------------------------------------------------------------------
+    def downsample_dev(self, x_ptr, n, R, out_ptr):
+        _check(self.lib, self.lib.dfk_downsample_dev(self._h, x_ptr, int(n), int(R), out_ptr))
+
+    def downsample_host(self, x, R):
+        x, xp = _host_array(x)
+        out = np.empty(x.size // int(R), dtype=np.float64)
+        _check(self.lib, self.lib.dfk_downsample_host(self._h, xp, x.size, int(R), out.ctypes.data))
+        return out
+
+    def lpsd_dev(self, x_ptr, N, stride, C, ld_c, fs, opts=None) -> dict:
+        """Spectra of C device-resident series; returns host arrays f[nf], ps[C, nf], psd[C, nf], enbw[nf], navs[nf]."""
+        opts = opts if opts is not None else default_lpsd_opts()
+        nf = _i32()
+        _check(self.lib, self.lib.dfk_lpsd_plan(int(N), float(fs), ctypes.byref(opts), 0, ctypes.byref(nf), None, None,
+                                                None, None, None))
+        n = int(nf.value)
+        f, enbw, navs = np.empty(n), np.empty(n), np.empty(n, dtype=np.int64)
+        ps, psd = np.empty((int(C), n)), np.empty((int(C), n))
+        _check(self.lib, self.lib.dfk_lpsd_dev(self._h, x_ptr, int(N), int(stride), int(C), int(ld_c), float(fs),
+                                               ctypes.byref(opts), n, ctypes.byref(nf), f.ctypes.data, ps.ctypes.data,
+                                               psd.ctypes.data, enbw.ctypes.data, navs.ctypes.data))
+        return {"f": f, "ps": ps, "psd": psd, "enbw": enbw, "navs": navs}
 
     def set_host_slab_bytes(self, nbytes=0):
         """Slab size of the host-pointer entries (0: defaults); small values make a short record stream."""

@@ -41,6 +41,23 @@ class DeepFitObject:
         self.t0 = 0
         self.f_samp = self.f_mod = None
         self.ssq = self.amp = self.m = self.tau = self.phi = self.psi = self.dc = self.time = None
+        # spectral-estimate settings and results (data.py:148-158)
+        self.f = None
+        self.Sxx = None
+        self.olap = "default"
+        self.bmin = 1
+        self.Lmin = 0
+        self.Jdes = 500
+        self.Kdes = 100
+        self.order = 0
+        self.win = np.kaiser
+        self.psll = 200
+
+    def calc_lpsd(self):
+        """LPSD of the fitted interferometric phase (data.py:239-244), on the device."""
+        from .spectra import lpsd
+        self.f, _, self.Sxx, _, _, _ = lpsd(self.phi, self.fs, self.olap, self.bmin, self.Lmin, self.Jdes, self.Kdes,
+                                            self.order, self.win, self.psll, return_type="legacy")
 
 
 class DeepFitFramework:
@@ -55,6 +72,18 @@ class DeepFitFramework:
         raw.label = label
         self.raws[label] = raw
         return raw
+
+    def calc_lpsd(self, labels=None):
+        """LPSD of phi for the fits under ``labels``, or for every fit (core.py:590-609)."""
+        if labels is not None:
+            for label in labels:
+                try:
+                    self.fits[label].calc_lpsd()
+                except KeyError:
+                    logging.warning("Specified label is invalid!")
+        else:
+            for fit in self.fits.values():
+                fit.calc_lpsd()
 
     def fit_init(self, label, n):
         """(R, fs, nbuf) of a fitting run (core.py:390-422)."""

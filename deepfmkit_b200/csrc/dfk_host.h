@@ -1,0 +1,208 @@
+// Host-side internals shared by the translation units of libdfk_b200.so: the context, error reporting, scratch
+// buffers, the staged host -> device copy.  Not part of the ABI (include/dfk_b200.h is).
+#pragma once
+#include "../../include/dfk_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+
+inline thread_local char g_err[512] = "";
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DFK_CUDA(call)                                                                              \
+    do {                                                                                            \
+        const cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(DFK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+
+struct dfk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int smem_per_sm = 0;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr, aux_stream = nullptr, user_stream = nullptr;
+    bool use_user = false;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join = nullptr;
+    // pageable host records are staged through pinned buffers filled by a few copy threads
+    static constexpr int kStagers = 3;
+    static constexpr size_t kStageBytes = 64u << 20;
+    void* stager[kStagers] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
+    DevBuf qi, dc, retry, counters, slab[2], rows, stats, stats_part, misc, qi_seed, dc_seed;
+    static constexpr int kPostBufs = 6;
+    DevBuf post[kPostBufs];  // scratch of the ingest / spectra / generator entries (dfk_post.cu, dfk_ingest.cu)
+    int64_t launches = 0;
+    bool stats_ready = false;      // ctx->stats already holds whole-record moments (streamed EKF)
+    size_t host_slab_bytes = 0;    // 0 = defaults; else the slab size of the host-pointer entries (tests force streaming)
+    // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the
+    // demod launch [0], the LM launches [1], the side-stream seed fits [2] and the EKF kernel [3], summed on read
+    bool profiling = false;
+    static constexpr int kProfSlots = 512;
+    cudaEvent_t prof_ev[DFK_PROFILE_KINDS][kProfSlots][2] = {};
+    int prof_used[DFK_PROFILE_KINDS] = {};
+    double prof_ms[DFK_PROFILE_KINDS] = {};
+    int64_t prof_n[DFK_PROFILE_KINDS] = {};
+    cudaStream_t stream() const { return use_user ? user_stream : own_stream; }
+};
+
+
+inline int ensure(dfk_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes) return DFK_OK;
+    if (b.ptr) {
+        // scratch may still be in use by kernels queued on the stream
+        DFK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        DFK_CUDA(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    const size_t want = std::max(bytes, static_cast<size_t>(256));
+    const cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) {
+        b.ptr = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? DFK_ERR_NOMEM : DFK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want,
+                    cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return DFK_OK;
+}
+
+inline int prof_drain(dfk_ctx* ctx) {  // fold recorded event pairs into the totals (synchronises)
+    for (int k = 0; k < DFK_PROFILE_KINDS; ++k) {
+        for (int i = 0; i < ctx->prof_used[k]; ++i) {
+            DFK_CUDA(cudaEventSynchronize(ctx->prof_ev[k][i][1]));
+            float ms = 0.f;
+            DFK_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[k][i][0], ctx->prof_ev[k][i][1]));
+            ctx->prof_ms[k] += ms;
+            ctx->prof_n[k]++;
+        }
+        ctx->prof_used[k] = 0;
+    }
+    return DFK_OK;
+}
+
+struct ProfScope {  // records an event pair around the launches issued while it lives
+    dfk_ctx* ctx;
+    int kind, slot;
+    cudaStream_t st;
+    ProfScope(dfk_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), slot(-1), st(s) {
+        if (!ctx->profiling) return;
+        if (ctx->prof_used[kind] == dfk_ctx::kProfSlots && prof_drain(ctx) != DFK_OK) return;
+        slot = ctx->prof_used[kind];
+        for (int e = 0; e < 2; ++e)
+            if (!ctx->prof_ev[kind][slot][e] && cudaEventCreate(&ctx->prof_ev[kind][slot][e]) != cudaSuccess) {
+                slot = -1;
+                return;
+            }
+        cudaEventRecord(ctx->prof_ev[kind][slot][0], st);
+    }
+    ~ProfScope() {
+        if (slot < 0) return;
+        cudaEventRecord(ctx->prof_ev[kind][slot][1], st);
+        ctx->prof_used[kind] = slot + 1;
+    }
+};
+
+struct Guard {  // make the context's device current for the duration of a call
+    int prev = -1;
+    bool ok = false;
+    explicit Guard(const dfk_ctx* ctx) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~Guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Host-pointer entries enqueue DMA from caller memory and from the pinned stagers on three streams.  If such a call
+// leaves early on an error, everything already queued must drain before the caller may free or reuse its record.
+struct HostCallGuard {
+    dfk_ctx* ctx;
+    bool finished = false;
+    explicit HostCallGuard(dfk_ctx* c) : ctx(c) {}
+    void done() { finished = true; }
+    ~HostCallGuard() {
+        if (finished) return;
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamSynchronize(ctx->stream());
+    }
+};
+
+#define DFK_ENTER(ctx)                                             \
+    if (!(ctx)) return fail(DFK_ERR_ARG, "null context");          \
+    Guard guard_(ctx);                                             \
+    if (!guard_.ok) return fail(DFK_ERR_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
+inline bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+inline void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = static_cast<int>(std::min<size_t>(hw ? std::min(hw, 16u) : 4u, bytes / (4u << 20) + 1));
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t chunk = ((bytes / nt) + 4095) & ~static_cast<size_t>(4095);
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, chunk * t), hi = std::min(bytes, chunk * (t + 1));
+        if (hi > lo)
+            pool.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+// Host -> device copy of one slab on the copy stream.  Pinned (or registered) memory goes by DMA directly; pageable
+// memory -- what a numpy array from pandas is -- would make cudaMemcpyAsync stage it synchronously at ~10 GB/s, so
+// it is copied by a few threads into pinned staging buffers whose DMA overlaps the next buffer's fill.
+inline int copy_slab_to_device(dfk_ctx* ctx, void* dst, const void* src, size_t bytes, bool pageable) {
+    if (!pageable) {
+        DFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        return DFK_OK;
+    }
+    for (int i = 0; i < dfk_ctx::kStagers; ++i) {
+        if (!ctx->stager[i]) {
+            DFK_CUDA(cudaHostAlloc(&ctx->stager[i], dfk_ctx::kStageBytes, cudaHostAllocDefault));
+            DFK_CUDA(cudaEventCreateWithFlags(&ctx->stager_free[i], cudaEventDisableTiming));
+        }
+    }
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += dfk_ctx::kStageBytes, k = (k + 1) % dfk_ctx::kStagers) {
+        const size_t n = std::min(dfk_ctx::kStageBytes, bytes - off);
+        DFK_CUDA(cudaEventSynchronize(ctx->stager_free[k]));  // (a never-recorded event counts as complete)
+        parallel_memcpy(ctx->stager[k], static_cast<const char*>(src) + off, n);
+        DFK_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->stager[k], n, cudaMemcpyHostToDevice, ctx->copy_stream));
+        DFK_CUDA(cudaEventRecord(ctx->stager_free[k], ctx->copy_stream));
+    }
+    return DFK_OK;
+}

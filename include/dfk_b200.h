@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DFK_ABI_VERSION 2
+#define DFK_ABI_VERSION 3
 #define DFK_ROW_STRIDE 8
 #define DFK_MAX_HARMONICS 64
 
@@ -85,6 +85,18 @@ typedef struct dfk_lm_counters {
     uint64_t n_grid;    /* grid-search fallbacks       (fit.py:260)         */
     uint64_t n_bessel_steps; /* Miller recurrence steps over all evaluations */
 } dfk_lm_counters;
+
+/* Settings of the log-frequency spectral estimate; defaults of DeepFitObject (data.py:150-158). */
+typedef struct dfk_lpsd_opts {
+    double olap;     /* overlap fraction; < 0 = "default": the window's recommended overlap (data.py:150) */
+    double bmin;     /* first usable (fractional) DFT bin                                  (1)   */
+    int64_t lmin;    /* shortest segment                                                   (0)   */
+    int32_t jdes;    /* desired number of frequencies                                      (500) */
+    int32_t kdes;    /* desired number of averages                                         (100) */
+    int32_t order;   /* detrending polynomial per segment: -1 none, 0 mean, 1, 2           (0)   */
+    int32_t window;  /* 0 = Kaiser (np.kaiser, data.py:156), 1 = Hann                      (0)   */
+    double psll;     /* Kaiser peak side-lobe level in dB                                  (200) */
+} dfk_lpsd_opts;
 
 typedef struct dfk_ctx dfk_ctx;
 
@@ -198,6 +210,28 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
 /* Slab size of the two host-pointer entries above (0 restores the defaults: 128 MiB NLS slabs, half the free
  * device memory for the EKF).  Lets a small record exercise the streaming path. */
 int dfk_set_host_slab_bytes(dfk_ctx* ctx, int64_t bytes);
+
+/* ---- post-fit step -------------------------------------------------------------- */
+/* Block means: out[b] = mean(x[b*R .. b*R+R-1]), b < n / R; a tail shorter than R is dropped.
+ * Replaces vectorized_downsample (dsp.py:3-56), the boxcar that brings the simulated ground-truth phase to the
+ * fit rate.  The host entry streams the record in slabs like dfk_nls_fit_host. */
+int dfk_downsample_dev(dfk_ctx* ctx, const double* x_dev, int64_t n, int64_t R, double* out_dev);
+int dfk_downsample_host(dfk_ctx* ctx, const double* x_host, int64_t n, int64_t R, double* out_host);
+
+void dfk_default_lpsd_opts(dfk_lpsd_opts* o);
+/* The frequency plan of the estimate for a series of N samples at rate fs: frequencies f, resolutions r,
+ * fractional bins m, segment lengths L, averages K (the LTPDA ltf_plan scheduler).  *nf receives the number of
+ * frequencies; at most cap entries are written to each non-NULL array. */
+int dfk_lpsd_plan(int64_t N, double fs, const dfk_lpsd_opts* opts, int32_t cap, int32_t* nf, double* f, double* r,
+                  double* m, int64_t* L, int64_t* K);
+/* Log-frequency power spectrum / spectral density of C device-resident series (Troebs & Heinzel 2006).
+ * Replaces the spectools.lpsd call of calc_lpsd (core.py:590-609, data.py:239-244) on fit.phi.  Sample i of series c
+ * is x_dev[c * ld_c + i * stride] -- stride = DFK_ROW_STRIDE reads a column of a row table in place.
+ * Host outputs: f_host[nf], ps_host / psd_host [C x nf] (power spectrum; one-sided density, the reference's Sxx),
+ * enbw_host[nf], navs_host[nf]; any may be NULL.  Fails if the plan needs more than cap frequencies. */
+int dfk_lpsd_dev(dfk_ctx* ctx, const double* x_dev, int64_t N, int64_t stride, int64_t C, int64_t ld_c, double fs,
+                 const dfk_lpsd_opts* opts, int32_t cap, int32_t* nf_out, double* f_host, double* ps_host,
+                 double* psd_host, double* enbw_host, int64_t* navs_host);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 /* Counters accumulated by the LM kernels since the last reset (device -> host copy, syncs). */
