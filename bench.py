@@ -542,9 +542,9 @@ def strong_scaling(torch, dist, ctx, local, rank, world, w0, opts, single_gpu_ms
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        rows = nls_fit_batch(xc, 200e3, F_MOD, 20, ndata=10, seeded=True, device=local)
+        rows = nls_fit_batch(xc, 200e3, F_MOD, 20, ndata=10, seeded=True, device=local, return_tensor=True)
         flat = rows.reshape(chi - clo, -1)
-        tab = gather_rows(flat, C, dst=0)
+        tab = gather_rows(flat, C, dst=0)  # GPU to GPU over NVLink, then one D2H of the 82 MB table on rank 0
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -560,10 +560,10 @@ def strong_scaling(torch, dist, ctx, local, rank, world, w0, opts, single_gpu_ms
             "cfg2_one_record": {"buffers": NBUF, "wall_ms": rec_s * 1e3, "buffers_per_sec": NBUF / rec_s,
                                 "single_gpu_kernel_ms": single_gpu_ms,
                                 "includes": "rank-0 fit of buffer 0, 32-byte seed broadcast, slab kernels on every rank, "
-                                            "D2H of each rank's rows, gather of the 11.5 MB row table on rank 0 (host wall "
-                                            "clock, max over ranks)"},
+                                            "NCCL gather of the rows to rank 0 (GPU to GPU), one D2H of the 11.5 MB table (host "
+                                            "wall clock, max over ranks)"},
             "cfg3_wave_by_channel": {"buffers": nb3, "wall_ms": wave_s * 1e3, "buffers_per_sec": nb3 / wave_s,
-                                     "includes": "per-rank batched readout of its channels, D2H rows, gather on rank 0"}}
+                                     "includes": "per-rank batched readout of its channels, NCCL gather to rank 0, one D2H of the 82 MB table"}}
 
 
 # ---- GPU arm --------------------------------------------------------------------------------------------

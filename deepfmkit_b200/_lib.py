@@ -38,6 +38,14 @@ class EkfOpts(ctypes.Structure):
                 ("q_diag", ctypes.c_double * 5), ("r_val", ctypes.c_double), ("init_dc", ctypes.c_double)]
 
 
+class RawHeader(ctypes.Structure):
+    _fields_ = [("channels", ctypes.c_int32), ("pad_", ctypes.c_int32), ("t0", ctypes.c_int64),
+                ("f_samp", ctypes.c_double), ("f_mod", ctypes.c_double), ("data_offset", ctypes.c_int64)]
+
+
+RAW_DTYPES = {"int16": 0, "int32": 1, "float32": 2, "float64": 3}
+
+
 class LpsdOpts(ctypes.Structure):
     _fields_ = [("olap", ctypes.c_double), ("bmin", ctypes.c_double), ("lmin", ctypes.c_int64),
                 ("jdes", ctypes.c_int32), ("kdes", ctypes.c_int32), ("order", ctypes.c_int32),
@@ -81,6 +89,14 @@ SYMBOLS = {
     "dfk_nls_fit_seeded_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
     "dfk_set_host_slab_bytes": (ctypes.c_int, [_vp, _i64]),
+    "dfk_raw_parse_header": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(RawHeader)]),
+    "dfk_text_load_file": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "dfk_text_load_host": (ctypes.c_int, [_vp, _vp, _i64, ctypes.POINTER(_i64)]),
+    "dfk_text_parse_dev": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i64, ctypes.POINTER(_i64)]),
+    "dfk_text_release": (ctypes.c_int, [_vp]),
+    "dfk_widen_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
+    "dfk_ingest_binary_host": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
+    "dfk_ingest_binary_file": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_downsample_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_downsample_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_default_lpsd_opts": (None, [ctypes.POINTER(LpsdOpts)]),
@@ -159,6 +175,15 @@ def default_lpsd_opts() -> LpsdOpts:
     o = LpsdOpts()
     load_library().dfk_default_lpsd_opts(ctypes.byref(o))
     return o
+
+
+def raw_parse_header(path) -> dict:
+    """Header of a DFMSWPM raw_data file (host only): channels, t0, f_samp, f_mod, data_offset."""
+    lib = load_library()
+    h = RawHeader()
+    _check(lib, lib.dfk_raw_parse_header(os.fsencode(path), ctypes.byref(h)))
+    return {"channels": int(h.channels), "t0": int(h.t0), "f_samp": float(h.f_samp), "f_mod": float(h.f_mod),
+            "data_offset": int(h.data_offset)}
 
 
 def lpsd_plan(N, fs, opts=None) -> dict:
@@ -315,6 +340,47 @@ class Context:
         _check(self.lib, self.lib.dfk_ekf_host(self._h, zp, T, C, int(R), float(f_samp), float(f_mod),
                                                ctypes.byref(opts) if opts is not None else None, rows.ctypes.data))
         return rows
+
+    # ---- raw-data ingest ---------------------------------------------------------------------------------
+    def text_load_file(self, path, byte_offset=0):
+        """Upload the data region of a text file and index its rows. Returns (nbytes, nrows)."""
+        nb, nr = _i64(), _i64()
+        _check(self.lib, self.lib.dfk_text_load_file(self._h, os.fsencode(path), int(byte_offset), ctypes.byref(nb),
+                                                     ctypes.byref(nr)))
+        return int(nb.value), int(nr.value)
+
+    def text_load_host(self, text: bytes):
+        nr = _i64()
+        buf = ctypes.create_string_buffer(text, len(text)) if len(text) else None
+        _check(self.lib, self.lib.dfk_text_load_host(self._h, ctypes.cast(buf, _vp) if buf is not None else None,
+                                                     len(text), ctypes.byref(nr)))
+        return int(nr.value)
+
+    def text_parse_dev(self, ncols, out_ptr, ld_c, usecols=None):
+        """Parse the resident text into out_ptr[c * ld_c + r]. Returns the number of bad (NaN) fields."""
+        nbad = _i64()
+        cols = (ctypes.c_int32 * int(ncols))(*[int(c) for c in usecols]) if usecols is not None else None
+        _check(self.lib, self.lib.dfk_text_parse_dev(self._h, int(ncols), cols, out_ptr, int(ld_c), ctypes.byref(nbad)))
+        return int(nbad.value)
+
+    def text_release(self):
+        _check(self.lib, self.lib.dfk_text_release(self._h))
+
+    def widen_dev(self, src_ptr, dtype, T, C, time_major, out_ptr, ld_c, scale=1.0, offset=0.0):
+        _check(self.lib, self.lib.dfk_widen_dev(self._h, src_ptr, RAW_DTYPES[str(dtype)], int(T), int(C),
+                                                int(bool(time_major)), float(scale), float(offset), out_ptr, int(ld_c)))
+
+    def ingest_binary_host(self, src, T, C, time_major, out_ptr, ld_c, scale=1.0, offset=0.0):
+        """src: contiguous numpy array of int16 / int32 / float32 / float64 holding T * C samples."""
+        src = np.ascontiguousarray(src)
+        _check(self.lib, self.lib.dfk_ingest_binary_host(self._h, src.ctypes.data, RAW_DTYPES[src.dtype.name], int(T),
+                                                         int(C), int(bool(time_major)), float(scale), float(offset),
+                                                         out_ptr, int(ld_c)))
+
+    def ingest_binary_file(self, path, byte_offset, dtype, T, C, time_major, out_ptr, ld_c, scale=1.0, offset=0.0):
+        _check(self.lib, self.lib.dfk_ingest_binary_file(self._h, os.fsencode(path), int(byte_offset),
+                                                         RAW_DTYPES[str(dtype)], int(T), int(C), int(bool(time_major)),
+                                                         float(scale), float(offset), out_ptr, int(ld_c)))
 
     # ---- post-fit step ---------------------------------------------------------------------------------
     def downsample_dev(self, x_ptr, n, R, out_ptr):

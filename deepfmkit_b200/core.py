@@ -16,19 +16,43 @@ from .fitters import EKFFitter, StandardNLSFitter
 
 
 class DeepRawObject:
-    """One channel of raw data: what the fitters read (data.py:16-118 holds the full container)."""
+    """One channel of raw data: what the fitters read (data.py:16-118 holds the full container).
 
-    def __init__(self, data=None, f_samp=None, f_mod=None, label=None, sim=None, t0=0):
+    ``data`` is the one-column pandas frame of the reference.  A record that already lives on the GPU (io.load_raw,
+    io.load_binary, the device generator) is carried as ``device_data`` -- a 1-D float64 CUDA tensor the fitters read
+    in place -- and the frame is built from it only when ``data`` is asked for."""
+
+    def __init__(self, data=None, f_samp=None, f_mod=None, label=None, sim=None, t0=0, device_data=None, column="ch0"):
         import pandas as pd
         if data is not None and not hasattr(data, "columns"):
-            data = pd.DataFrame(np.asarray(data, dtype=np.float64).reshape(-1), columns=["ch0"])
-        self.data = data
+            data = pd.DataFrame(np.asarray(data, dtype=np.float64).reshape(-1), columns=[column])
+        self._data = data
+        self.device_data = device_data
+        self._column = column
         self.f_samp = f_samp
         self.f_mod = f_mod
         self.label = label
         self.sim = sim
         self.t0 = t0
         self.phi_sim = None
+        self.raw_file = None
+
+    @property
+    def data(self):
+        if self._data is None and self.device_data is not None:
+            import pandas as pd
+            self._data = pd.DataFrame(self.device_data.detach().cpu().numpy().reshape(-1), columns=[self._column])
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self.device_data = None  # the frame is the truth once somebody assigns it
+
+    def __len__(self):
+        if self.device_data is not None:
+            return int(self.device_data.shape[0])
+        return 0 if self._data is None else int(self._data.shape[0])
 
 
 class DeepFitObject:
@@ -62,10 +86,37 @@ class DeepFitObject:
 
 class DeepFitFramework:
     def __init__(self):
+        self.raw_file = None
         self.sims = {}
         self.raws = {}
         self.fits = {}
         self.fits_df = {}
+
+    def parse_header(self, file_select="raw"):
+        """Header of ``self.raw_file`` (core.py:129-174, raw files only: fit files stay with the reference)."""
+        if file_select != "raw" or getattr(self, "raw_file", None) is None:
+            logging.error("No files specified !!")
+            return
+        from .io import parse_header
+        hdr = parse_header(self.raw_file)
+        self.channr, self.t0, self.f_samp, self.f_mod = hdr["channels"], hdr["t0"], hdr["f_samp"], hdr["f_mod"]
+        logging.info("Number of channels: {}".format(self.channr))
+        logging.info("Starting time: {}".format(self.t0))
+        logging.info("Sampling frequency: {}".format(self.f_samp))
+        logging.info("Modulation frequency: {}".format(self.f_mod))
+
+    def load_raw(self, raw_file=None, labels=None):
+        """Load a raw_data file (core.py:259-286): parsed on the GPU, one ``DeepRawObject`` per channel whose samples
+        stay on the device for the fitters."""
+        from .io import load_raw
+        if raw_file is not None:
+            self.raw_file = raw_file
+        if getattr(self, "raw_file", None) is None:
+            logging.error("No raw file specified !!")
+            return
+        self.parse_header(file_select="raw")
+        for raw in load_raw(self.raw_file, labels=labels):
+            self.raws[raw.label] = raw
 
     def load_raw_object(self, raw: DeepRawObject, label=None):
         label = label or raw.label
@@ -90,7 +141,7 @@ class DeepFitFramework:
         raw = self.raws[label]
         R = int(raw.f_samp / raw.f_mod * n)
         fs = raw.f_samp / R
-        nbuf = int(raw.data.shape[0] / R)
+        nbuf = int(len(raw) / R)
         if nbuf == 0:
             logging.error("Check buffer size !! Calculated nbuf is zero.")
         return R, fs, nbuf

@@ -54,6 +54,9 @@ struct dfk_ctx {
     static constexpr int kPostBufs = 6;
     DevBuf post[kPostBufs];  // scratch of the ingest / spectra / generator entries (dfk_post.cu, dfk_ingest.cu)
     int64_t launches = 0;
+    // text record resident in post[3] between dfk_text_load* and dfk_text_parse_dev (dfk_ingest.cu)
+    int64_t text_bytes = 0, text_rows = 0, text_chunks = 0;
+    int text_first = 0;
     bool stats_ready = false;      // ctx->stats already holds whole-record moments (streamed EKF)
     size_t host_slab_bytes = 0;    // 0 = defaults; else the slab size of the host-pointer entries (tests force streaming)
     // optional per-kernel-class timing (bench.py's roofline figures): event pairs recorded around the

@@ -44,7 +44,21 @@ def _calculate_fit_params(main_raw, n):
     return R, fs, nbuf
 
 
+def _device_record(main_raw):
+    """The channel's samples as a 1-D float64 CUDA tensor when the record already lives on a GPU, else None."""
+    t = getattr(main_raw, "device_data", None)
+    if t is None:
+        return None
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
+        return None
+    return t.contiguous().view(-1)
+
+
 def _record_length(main_raw):
+    t = _device_record(main_raw)
+    if t is not None:
+        return int(t.shape[0])
     data = main_raw.data
     return int(data.shape[0])
 
@@ -101,11 +115,24 @@ class StandardNLSFitter(BaseFitter):
         R, _, nbuf = _calculate_fit_params(main_raw, n)
         if nbuf == 0:
             return pd.DataFrame()
-        x = _record_values(main_raw)[: nbuf * R]  # the reference's reshape(-1, R) raises on a ragged tail (Q7)
         w0 = 2.0 * np.pi * main_raw.f_mod / main_raw.f_samp  # fitters.py:39
+        opts = fit_tunables.current_lm_opts(kwargs.get("tunables_from"))
+        xd = _device_record(main_raw)
+        if xd is not None:  # record already on a GPU (io.load_raw / load_binary): fitted where it lies
+            import torch
+            ctx = _lib.get_context(xd.device.index)
+            rows_d = torch.empty((nbuf, _lib.ROW_STRIDE), dtype=torch.float64, device=xd.device)
+            with torch.cuda.device(xd.device):
+                ctx.use_torch_stream()
+                try:
+                    ctx.nls_fit_dev(xd.data_ptr(), nbuf, R, int(ndata), w0, [init_a, init_m, 0.0, init_psi], chunks, opts,
+                                    rows_d.data_ptr())
+                finally:
+                    ctx.use_default_stream()
+            return rows_to_frame(rows_d.cpu().numpy())
+        x = _record_values(main_raw)[: nbuf * R]  # the reference's reshape(-1, R) raises on a ragged tail (Q7)
         ctx = _lib.get_context(device)
-        rows = ctx.nls_fit_host(x, R, int(ndata), w0, [init_a, init_m, 0.0, init_psi], seeded=chunks,
-                                opts=fit_tunables.current_lm_opts(kwargs.get("tunables_from")))
+        rows = ctx.nls_fit_host(x, R, int(ndata), w0, [init_a, init_m, 0.0, init_psi], seeded=chunks, opts=opts)
         return rows_to_frame(rows)
 
 
@@ -130,8 +157,22 @@ class EKFFitter(BaseFitter):
         opts.r_val = float("nan") if r_val is None else float(r_val)  # NaN -> var(record), fitters.py:256
         device = kwargs.get("device", 0)
 
-        z = _record_values(main_raw, column="ch0")  # the reference reads column "ch0" by name (fitters.py:238)
         R, _, nbuf = _calculate_fit_params(main_raw, n)
+        zd = _device_record(main_raw)
+        if zd is not None:
+            import torch
+            ctx = _lib.get_context(zd.device.index)
+            rows_d = torch.empty((nbuf, _lib.ROW_STRIDE), dtype=torch.float64, device=zd.device)
+            with torch.cuda.device(zd.device):
+                ctx.use_torch_stream()
+                try:
+                    T = int(zd.shape[0])
+                    ctx.ekf_dev(zd.data_ptr(), T, 1, 1, T, R, float(main_raw.f_samp), float(main_raw.f_mod), opts,
+                                rows_d.data_ptr())
+                finally:
+                    ctx.use_default_stream()
+            return rows_to_frame(rows_d.cpu().numpy())
+        z = _record_values(main_raw, column="ch0")  # the reference reads column "ch0" by name (fitters.py:238)
         ctx = _lib.get_context(device)
         rows = ctx.ekf_host(z[None, :], R, main_raw.f_samp, main_raw.f_mod, opts)[0]
         return rows_to_frame(rows)

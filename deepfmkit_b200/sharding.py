@@ -36,31 +36,39 @@ def broadcast_seed(seed_row, src: int = 0, group=None):
     return t.cpu().numpy()
 
 
-def gather_rows(local_rows: np.ndarray, n_units: int, dst: int = 0, group=None):
-    """Gather per-rank row blocks [hi-lo, 8] into one [n_units, 8] table on ``dst`` (None elsewhere)."""
+def gather_rows(local_rows, n_units: int, dst: int = 0, group=None, return_tensor: bool = False):
+    """Gather per-rank row blocks [hi-lo, W] into one [n_units, W] table on ``dst`` (None elsewhere).
+
+    ``local_rows`` may be a numpy array or a torch tensor.  Under nccl a CUDA tensor is gathered where it lies --
+    GPU to GPU over NVLink, no host staging -- and the table comes back to the host in one copy (or stays on the
+    device with ``return_tensor``); under gloo everything is host memory."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     bounds = all_slab_bounds(n_units, world)
-    width = local_rows.shape[1] if local_rows.ndim == 2 else 8
-    longest = max(hi - lo for lo, hi in bounds)
-    pad = np.zeros((longest, width), dtype=np.float64)
-    pad[: local_rows.shape[0]] = local_rows
-    t = torch.from_numpy(pad)
     on_gpu = dist.get_backend(group) == "nccl"
-    if on_gpu:
-        t = t.cuda()
+    t = local_rows if isinstance(local_rows, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local_rows, dtype=np.float64))
+    if t.dim() != 2:
+        t = t.reshape(-1, 8)
+    t = t.cuda() if on_gpu else t.cpu()
+    width = t.shape[1]
+    longest = max(hi - lo for lo, hi in bounds)
+    if t.shape[0] != longest:  # ragged split: pad to the longest block
+        pad = torch.zeros((longest, width), dtype=torch.float64, device=t.device)
+        pad[: t.shape[0]] = t
+        t = pad
+    t = t.contiguous()
     out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
     dist.gather(t, out, dst=dst, group=group)
     if rank != dst:
         return None
-    parts = [o.cpu().numpy()[: hi - lo] for o, (lo, hi) in zip(out, bounds)]
-    return np.concatenate(parts, axis=0)
+    table = torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, bounds)], dim=0)
+    return table if return_tensor else table.cpu().numpy()
 
 
 def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, group=None, tunables_from=None,
-                    chunks_per_rank=1, gather=True):
+                    chunks_per_rank=1, gather=True, return_tensor=False):
     """NLS readout of one long record sharded over the ranks of ``group`` as contiguous buffer-aligned slabs.
 
     Every rank calls this with *its* slab: ``x_slab`` holds buffers ``slab_bounds(n_buffers_total, world, rank)``
@@ -108,7 +116,7 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
                 torch.cuda.current_stream(dev).synchronize()
             finally:
                 ctx.use_default_stream()
-        local = rows.cpu().numpy()
+        local = rows  # stays on the device: the gather below is GPU to GPU
     else:
         xs = np.ascontiguousarray(np.asarray(x_slab, dtype=np.float64)).reshape(-1)
         if xs.size < nb * R:
@@ -124,8 +132,8 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
                 local[first:] = ctx.nls_fit_seeded_host(xs[first * R: nb * R], R, ndata, w0, seed, chunks=chunks_per_rank,
                                                         opts=opts)
     if not gather:
-        return local
-    return gather_rows(local, n_buffers_total, dst=0, group=group)
+        return local if (return_tensor or not isinstance(local, torch.Tensor)) else local.cpu().numpy()
+    return gather_rows(local, n_buffers_total, dst=0, group=group, return_tensor=return_tensor)
 
 
 def ekf_fit_sharded(z_channels, n_channels_total, f_samp, f_mod, n, device=None, group=None, **ekf_kwargs):
@@ -145,7 +153,7 @@ def ekf_fit_sharded(z_channels, n_channels_total, f_samp, f_mod, n, device=None,
     z = np.atleast_2d(np.asarray(z_channels, dtype=np.float64)) if not isinstance(z_channels, torch.Tensor) else z_channels
     if z.shape[0] != hi - lo:
         raise ValueError(f"rank {rank}: got {z.shape[0]} channels, owns {hi - lo}")
-    rows = ekf_fit_batch(z, f_samp, f_mod, n, device=device, **ekf_kwargs) if hi > lo else np.zeros((0, 0, 8))
+    rows = ekf_fit_batch(z, f_samp, f_mod, n, device=device, return_tensor=True, **ekf_kwargs) if hi > lo else np.zeros((0, 0, 8))
     nbuf = rows.shape[1] if hi > lo else 0
     sizes = [None] * world
     dist.all_gather_object(sizes, nbuf, group=group)

@@ -98,6 +98,22 @@ typedef struct dfk_lpsd_opts {
     double psll;     /* Kaiser peak side-lobe level in dB                                  (200) */
 } dfk_lpsd_opts;
 
+/* Header of a DFMSWPM raw_data text file as parse_header reads it (core.py:129-174). */
+typedef struct dfk_raw_header {
+    int32_t channels;     /* "Number of channels" (line 2)        */
+    int32_t pad_;
+    int64_t t0;           /* "Start time" (line 3)                */
+    double f_samp;        /* "Sampling frequency" (line 4)        */
+    double f_mod;         /* "Modulation frequency" (line 5)      */
+    int64_t data_offset;  /* byte offset of the first data row: after the 13 lines read_csv(skiprows=13) skips */
+} dfk_raw_header;
+
+/* Sample types of the binary ingest path. */
+#define DFK_RAW_I16 0
+#define DFK_RAW_I32 1
+#define DFK_RAW_F32 2
+#define DFK_RAW_F64 3
+
 typedef struct dfk_ctx dfk_ctx;
 
 /* ---- library / context ------------------------------------------------------------------ */
@@ -210,6 +226,39 @@ int dfk_ekf_host(dfk_ctx* ctx, const double* z_host, int64_t T, int64_t C, int64
 /* Slab size of the two host-pointer entries above (0 restores the defaults: 128 MiB NLS slabs, half the free
  * device memory for the EKF).  Lets a small record exercise the streaming path. */
 int dfk_set_host_slab_bytes(dfk_ctx* ctx, int64_t bytes);
+
+/* ---- raw-data ingest ------------------------------------------------------------- */
+/* parse_header(file_select='raw') (core.py:129-174): of header lines 2..5 only the characters "0-9." are kept
+ * and read as int, int, float, float (an exponent or a sign is therefore dropped, as in the reference); fails where
+ * Python's int()/float() would raise.  Host only -- no GPU needed. */
+int dfk_raw_parse_header(const char* path, dfk_raw_header* out);
+
+/* load_raw (core.py:259-286) is pd.read_csv(raw_file, sep=' ', skiprows=13, usecols=[c], names=['ch<c>']) per
+ * channel.  Here the data region of the file goes to the device once (file -> pinned staging buffers -> HBM, reads and
+ * DMA overlapped) and is parsed there: dfk_text_load_* uploads the bytes, finds the rows (lines holding only blanks
+ * are skipped) and reports their number, so that the caller can allocate the record; dfk_text_parse_dev converts
+ * the wanted columns into out_dev (column c, row r at out_dev[c * ld_c + r]).  usecols: ascending file columns, or
+ * NULL for 0..ncols-1.  Fields are converted exactly as the reference's pandas call converts them (pandas' C-parser
+ * default, precise_xstrtod: 17 significant digits, one scaling by a power of ten -- not correctly rounded, and
+ * reproduced bit for bit).  A missing or non-numeric field becomes NaN and is counted in *nbad_out.
+ * The text stays resident (for further dfk_text_parse_dev calls) until the next load or dfk_text_release. */
+int dfk_text_load_file(dfk_ctx* ctx, const char* path, int64_t byte_offset, int64_t* nbytes_out, int64_t* nrows_out);
+int dfk_text_load_host(dfk_ctx* ctx, const char* text_host, int64_t nbytes, int64_t* nrows_out);
+int dfk_text_parse_dev(dfk_ctx* ctx, int32_t ncols, const int32_t* usecols, double* out_dev, int64_t ld_c,
+                       int64_t* nbad_out);
+int dfk_text_release(dfk_ctx* ctx);
+
+/* Binary fast path (additive: the reference reads text only): samples of type dtype (DFK_RAW_*), time-major
+ * interleaved (sample (t, c) at t * C + c, what acquisition hardware writes) or channel-major (c * T + t), widened
+ * to the fp64 channel-major record out_dev[c * ld_c + t] = scale * sample + offset.  The host and file entries
+ * stream the source in slabs through the pinned staging buffers, copies overlapping the widening kernel; a 16-bit
+ * record crosses PCIe at a quarter of the fp64 bytes. */
+int dfk_widen_dev(dfk_ctx* ctx, const void* src_dev, int32_t dtype, int64_t T, int64_t C, int32_t time_major,
+                  double scale, double offset, double* out_dev, int64_t ld_c);
+int dfk_ingest_binary_host(dfk_ctx* ctx, const void* src_host, int32_t dtype, int64_t T, int64_t C, int32_t time_major,
+                           double scale, double offset, double* out_dev, int64_t ld_c);
+int dfk_ingest_binary_file(dfk_ctx* ctx, const char* path, int64_t byte_offset, int32_t dtype, int64_t T, int64_t C,
+                           int32_t time_major, double scale, double offset, double* out_dev, int64_t ld_c);
 
 /* ---- post-fit step -------------------------------------------------------------- */
 /* Block means: out[b] = mean(x[b*R .. b*R+R-1]), b < n / R; a tail shorter than R is dropped.
