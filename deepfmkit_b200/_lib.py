@@ -18,6 +18,8 @@ ROW_STRIDE = 8
 MAX_HARMONICS = 64
 ABI_VERSION = 3
 PROFILE_KINDS = 4
+ASD_TRIAL_DOUBLES = 35
+TRIAL_STATS_DOUBLES = 6
 SCHED_INDEPENDENT = 0   # every buffer a cold start from init
 SCHED_EACH = -1         # every buffer its own chunk, seeded from buffer 0 (pool schedule at n_cores >= nbuf - 1)
 ROW_COLUMNS = ("amp", "m", "phi", "psi", "dc", "ssq", "fitok")
@@ -97,6 +99,8 @@ SYMBOLS = {
     "dfk_widen_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_ingest_binary_host": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_ingest_binary_file": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
+    "dfk_synth_asd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _vp, _i64, _vp, _i64, _vp]),
+    "dfk_trial_stats_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _vp]),
     "dfk_downsample_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_downsample_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_default_lpsd_opts": (None, [ctypes.POINTER(LpsdOpts)]),
@@ -381,6 +385,15 @@ class Context:
         _check(self.lib, self.lib.dfk_ingest_binary_file(self._h, os.fsencode(path), int(byte_offset),
                                                          RAW_DTYPES[str(dtype)], int(T), int(C), int(bool(time_major)),
                                                          float(scale), float(offset), out_ptr, int(ld_c)))
+
+    # ---- batched experiments ---------------------------------------------------------------------------
+    def synth_asd_dev(self, trials_ptr, ntrials, N, f_samp, y_ptr, ld, tables_ptr=None, ntables=0, truth_ptr=None):
+        _check(self.lib, self.lib.dfk_synth_asd_dev(self._h, trials_ptr, int(ntrials), int(N), float(f_samp), tables_ptr,
+                                                    int(ntables), y_ptr, int(ld), truth_ptr))
+
+    def trial_stats_dev(self, values_ptr, npoints, ntrials, ncols, col_stride, out_ptr):
+        _check(self.lib, self.lib.dfk_trial_stats_dev(self._h, values_ptr, int(npoints), int(ntrials), int(ncols),
+                                                      int(col_stride), out_ptr))
 
     # ---- post-fit step ---------------------------------------------------------------------------------
     def downsample_dev(self, x_ptr, n, R, out_ptr):

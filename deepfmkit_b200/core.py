@@ -118,6 +118,34 @@ class DeepFitFramework:
         for raw in load_raw(self.raw_file, labels=labels):
             self.raws[raw.label] = raw
 
+    def load_sim(self, sim):
+        self.sims[sim.label] = sim
+
+    def simulate(self, main_label, n_seconds, mode="asd", witness_label=None, snr_db=None, trial_num=0, verbose=False):
+        """Simulate the channel ``self.sims[main_label]`` on the GPU (core.py:176-243 -> SignalGenerator.generate) and
+        store the record in ``self.raws``.  Witness channels belong to the W-DFMI fitters and are not generated."""
+        import time
+        from .simulation import simulate
+        t0 = time.time()
+        if main_label not in self.sims:
+            logging.error(f"Main simulation label '{main_label}' not found!")
+            return
+        if witness_label:
+            logging.error("Witness channels are outside this package (W-DFMI stays with the reference).")
+            return
+        if mode == "snr" and snr_db is None:
+            logging.error("SNR mode requires a value for 'snr_db'.")
+            logging.error("Simulation failed to generate data.")
+            return
+        if mode not in ("asd", "snr"):
+            logging.error(f"Unknown simulation mode: '{mode}'")
+            logging.error("Simulation failed to generate data.")
+            return
+        main_config = self.sims[main_label]
+        raw = simulate(main_config, n_seconds, mode=mode, snr_db=snr_db, trial_num=trial_num)
+        self.raws[raw.label] = raw
+        main_config.simtime = time.time() - t0
+
     def load_raw_object(self, raw: DeepRawObject, label=None):
         label = label or raw.label
         raw.label = label

@@ -260,6 +260,28 @@ int dfk_ingest_binary_host(dfk_ctx* ctx, const void* src_host, int32_t dtype, in
 int dfk_ingest_binary_file(dfk_ctx* ctx, const char* path, int64_t byte_offset, int32_t dtype, int64_t T, int64_t C,
                            int32_t time_major, double scale, double offset, double* out_dev, int64_t ld_c);
 
+/* ---- batched experiments ------------------------------------------------------------- */
+/* One Monte-Carlo trial of the 'asd'-mode physics (physics.py:615-722), DFK_ASD_TRIAL_DOUBLES doubles:
+ *   [0] amp  [1] visibility  [2] df  [3] 2 pi f_mod  [4] psi  [5] 2 pi c / wavelength  [6] ref_arml / c
+ *   [7] meas_arml / c  [8] phi wavelength / (2 pi)  [9] arml_mod_amp  [10] 2 pi arml_mod_f  [11] arml_mod_psi
+ *   [12] amp_n sqrt(fs/2)  [13] df_n sqrt(fs/2)  [14] noise key (the trial number)  [15] number of waveform terms
+ *   (0: the waveform is row [16] of the tables)  [17 + 3k ..] harmonic h_k, amplitude a_k, phase p_k of term k < 6:
+ *   g(theta) = sum_k a_k cos(h_k theta + p_k), normalised to max |g| = 1 over the trial. */
+#define DFK_ASD_TRIAL_DOUBLES 35
+#define DFK_TRIAL_STATS_DOUBLES 6
+/* The reference simulates every trial of an Experiment on its own (experiments.py:15-88 -> SignalGenerator.generate,
+ * mode 'asd'); here all trials of a batch are produced at once, N samples each: y_dev[j * ld + i].  tables_dev:
+ * ntables x N samples of host-evaluated waveforms for trials whose waveform is not a harmonic series.
+ * truth_dev (may be NULL) receives the ground-truth interferometric phase (raw.phi_sim).  White amplitude and
+ * modulation-depth noise only; statistically, not bitwise, the reference's MT19937 draws. */
+int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, int64_t N, double f_samp,
+                      const double* tables_dev, int64_t ntables, double* y_dev, int64_t ld, double* truth_dev);
+/* Per grid point and result column: nanmean, nanstd, nanmin, nanmax, "worst" (the trial farthest from the mean)
+ * and the number of finite trials -- the aggregation at the end of Experiment.run (experiments.py:432-446).
+ * values_dev[(p * ntrials + t) * col_stride + c]; out_dev[(p * ncols + c) * 6 + {0..5}]. */
+int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints, int64_t ntrials, int32_t ncols,
+                        int64_t col_stride, double* out_dev);
+
 /* ---- post-fit step -------------------------------------------------------------- */
 /* Block means: out[b] = mean(x[b*R .. b*R+R-1]), b < n / R; a tail shorter than R is dropped.
  * Replaces vectorized_downsample (dsp.py:3-56), the boxcar that brings the simulated ground-truth phase to the
