@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import numpy as np
 
-SPEED_OF_LIGHT = 299792458.0  # scipy.constants.c
+SPEED_OF_LIGHT = 299792458.0  # speed of light in m/s, the exact SI value the reference uses
 
 
 class LaserConfig:
