@@ -87,6 +87,9 @@ SYMBOLS = {
     "dfk_synth_snr_slab_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d,
                                               ctypes.c_uint64]),
     "dfk_synth_snr_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _d, _d, _d, _d, _d, _d, _d, _d, ctypes.c_uint64]),
+    "dfk_sweep_demod_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i32, _d, _d, _d, _d, _d, _d, _d, _d, ctypes.c_uint64, _vp, _vp]),
+    "dfk_nls_sweep_dev": (ctypes.c_int, [_vp, c_double_p, _i32, _i64, _i64, _i64, _i64, _i32, _d, _d, _d, _d, _d, _d, _d,
+                                         ctypes.c_uint64, _d, _d, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_seeded_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
@@ -100,7 +103,7 @@ SYMBOLS = {
     "dfk_ingest_binary_host": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_ingest_binary_file": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_synth_asd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _vp, _i64, _vp, _i64, _vp]),
-    "dfk_trial_stats_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _vp]),
+    "dfk_trial_stats_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _vp]),
     "dfk_downsample_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_downsample_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_default_lpsd_opts": (None, [ctypes.POINTER(LpsdOpts)]),
@@ -308,6 +311,21 @@ class Context:
         _check(self.lib, self.lib.dfk_synth_snr_dev(self._h, x_ptr, T, C, f_samp, f_mod, m, amp, visibility, phi0,
                                                     dphi, psi0, snr_db, int(seed)))
 
+    def sweep_demod_dev(self, nbuf, c0, R, N, f_samp, f_mod, m, qi_ptr, dc_ptr, amp=1.0, visibility=1.0, phi0=0.0, psi0=0.0,
+                        snr_db=40.0, seed=0):
+        _check(self.lib, self.lib.dfk_sweep_demod_dev(self._h, int(nbuf), int(c0), int(R), int(N), float(f_samp),
+                                                      float(f_mod), float(m), amp, visibility, phi0, psi0, snr_db,
+                                                      int(seed), qi_ptr, dc_ptr))
+
+    def nls_sweep_dev(self, m_values, ntrials, trial0, seed_stride, R, N, f_samp, f_mod, rows_ptr, amp=1.0, visibility=1.0,
+                      phi0=0.0, psi0=0.0, snr_db=40.0, seed=0, init_a=1.6, init_m=None, opts=None):
+        ms = np.ascontiguousarray(m_values, dtype=np.float64)
+        _check(self.lib, self.lib.dfk_nls_sweep_dev(self._h, ms.ctypes.data_as(c_double_p), len(ms), int(ntrials), int(trial0),
+                                                    int(seed_stride), int(R), int(N), float(f_samp), float(f_mod), amp,
+                                                    visibility, phi0, psi0, snr_db, int(seed), float(init_a),
+                                                    float("nan") if init_m is None else float(init_m),
+                                                    ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
     def bessel_dev(self, x_ptr, n, nmax, out_ptr):
         _check(self.lib, self.lib.dfk_bessel_dev(self._h, x_ptr, n, nmax, out_ptr))
 
@@ -391,9 +409,9 @@ class Context:
         _check(self.lib, self.lib.dfk_synth_asd_dev(self._h, trials_ptr, int(ntrials), int(N), float(f_samp), tables_ptr,
                                                     int(ntables), y_ptr, int(ld), truth_ptr))
 
-    def trial_stats_dev(self, values_ptr, npoints, ntrials, ncols, col_stride, out_ptr):
+    def trial_stats_dev(self, values_ptr, npoints, ntrials, ncols, col_stride, out_ptr, center_ptr=None):
         _check(self.lib, self.lib.dfk_trial_stats_dev(self._h, values_ptr, int(npoints), int(ntrials), int(ncols),
-                                                      int(col_stride), out_ptr))
+                                                      int(col_stride), center_ptr, out_ptr))
 
     # ---- post-fit step ---------------------------------------------------------------------------------
     def downsample_dev(self, x_ptr, n, R, out_ptr):

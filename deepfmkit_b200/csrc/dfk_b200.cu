@@ -21,6 +21,7 @@
 #include "dfk_ekf_kernels.cuh"
 #include "dfk_lm_kernels.cuh"
 #include "dfk_synth.cuh"
+#include "dfk_sweep.cuh"
 
 #include "dfk_host.h"
 
@@ -1112,6 +1113,106 @@ int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, in
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
+}
+
+int dfk_sweep_demod_dev(dfk_ctx* ctx, int64_t nbuf, int64_t c0, int64_t R, int32_t N, double f_samp, double f_mod, double m,
+                        double amp, double visibility, double phi0, double psi0, double snr_db, uint64_t seed,
+                        double* qi_dev, double* dc_dev) {
+    DFK_ENTER(ctx);
+    if (nbuf < 0 || c0 < 0 || R <= 0) return fail(DFK_ERR_ARG, "bad geometry: nbuf=%lld R=%lld", (long long)nbuf, (long long)R);
+    if (N < 1 || N > DFK_MAX_HARMONICS) return fail(DFK_ERR_ARG, "harmonic count %d outside 1..%d", N, DFK_MAX_HARMONICS);
+    if (!(f_samp > 0.0) || !(f_mod > 0.0)) return fail(DFK_ERR_ARG, "f_samp and f_mod must be positive");
+    if (nbuf == 0) return DFK_OK;
+    if (!qi_dev || !dc_dev) return fail(DFK_ERR_ARG, "null pointer");
+    cudaStream_t st = ctx->stream();
+    const double per = f_samp / f_mod;
+    const bool whole = per == std::floor(per) && per >= 1.0;
+    const int64_t P = whole ? static_cast<int64_t>(per) : 0;
+    // fused path: one whole period per record, the geometry of the quarter-wave kernel, tables that fit the SM
+    if (whole && R == P && P <= dfk::kTileMaxPeriod && (P % 4) == 0 && !dev_int("DFK_NO_SWEEP_FUSE", 0)) {
+        const dfk::SweepSmem S = dfk::sweep_smem_layout(static_cast<int>(P), N);
+        if (S.total <= static_cast<size_t>(ctx->max_smem_optin)) {
+            dfk::SweepParams sp = {};
+            sp.synth.T = P;
+            sp.synth.C = nbuf;
+            sp.synth.P = P;
+            sp.synth.f_ratio = f_mod / f_samp;
+            sp.synth.m = m;
+            sp.synth.amp = amp;
+            sp.synth.vis = visibility;
+            sp.synth.phi0 = phi0;
+            sp.synth.psi0 = psi0;
+            sp.synth.sigma_scale = std::pow(10.0, -snr_db / 20.0);
+            sp.synth.seed = seed;
+            sp.phi = phi0;
+            sp.qi = qi_dev;
+            sp.dc = dc_dev;
+            sp.nbuf = nbuf;
+            sp.c0 = c0;
+            sp.N = N;
+            const int64_t ngroups = (nbuf + dfk::kPeriodNbw - 1) / dfk::kPeriodNbw;
+            const int grid = static_cast<int>(std::min<int64_t>((ngroups + dfk::kFoldConsumerWarps - 1) / dfk::kFoldConsumerWarps,
+                                                               ctx->sm_count));
+            DFK_CUDA(cudaFuncSetAttribute(dfk::sweep_period_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(S.total)));
+            ProfScope ps(ctx, 0, st);
+            dfk::sweep_period_kernel<<<grid, dfk::kSweepThreads, S.total, st>>>(sp);
+            ctx->launches++;
+            DFK_CUDA(cudaGetLastError());
+            return DFK_OK;
+        }
+    }
+    // any other geometry: records generated into scratch in waves, then the ordinary lock-in
+    const double w0 = 2.0 * dfk::kPi * f_mod / f_samp;
+    const int64_t per_wave = std::max<int64_t>(1, std::min<int64_t>(nbuf, (static_cast<int64_t>(256) << 20) / (R * 8)));
+    int rc = ensure(ctx, ctx->slab[0], static_cast<size_t>(per_wave) * R * 8);
+    if (rc) return rc;
+    double* x = static_cast<double*>(ctx->slab[0].ptr);
+    for (int64_t done = 0; done < nbuf; done += per_wave) {
+        const int64_t nw = std::min(per_wave, nbuf - done);
+        rc = dfk_synth_snr_slab_dev(ctx, x, R, nw, R, 0, f_samp, f_mod, m, amp, visibility, phi0, 0.0, psi0, snr_db,
+                                    seed + static_cast<uint64_t>(c0 + done));
+        if (rc) return rc;
+        ProfScope ps(ctx, 0, st);
+        rc = launch_demod(ctx, x, nw, 1, R, R, N, w0, qi_dev + done * 2 * N, dc_dev + done, st);
+        if (rc) return rc;
+    }
+    return DFK_OK;
+}
+
+int dfk_nls_sweep_dev(dfk_ctx* ctx, const double* m_values, int32_t nm, int64_t ntrials, int64_t trial0, int64_t seed_stride,
+                      int64_t R, int32_t N, double f_samp, double f_mod, double amp, double visibility, double phi0,
+                      double psi0, double snr_db, uint64_t seed, double init_a, double init_m, const dfk_lm_opts* opts,
+                      double* rows_dev) {
+    DFK_ENTER(ctx);
+    if (nm < 0 || ntrials < 0 || trial0 < 0) return fail(DFK_ERR_ARG, "bad sweep size");
+    if (nm == 0 || ntrials == 0) return DFK_OK;
+    if (!m_values || !rows_dev) return fail(DFK_ERR_ARG, "null pointer");
+    const int64_t nfit = static_cast<int64_t>(nm) * ntrials;
+    int rc = ensure(ctx, ctx->qi, static_cast<size_t>(nfit) * 2 * N * sizeof(double));
+    if (!rc) rc = ensure(ctx, ctx->dc, static_cast<size_t>(nfit) * sizeof(double));
+    if (!rc) rc = ensure(ctx, ctx->qi_seed, static_cast<size_t>(nm) * 4 * sizeof(double));
+    if (rc) return rc;
+    double* qi = static_cast<double*>(ctx->qi.ptr);
+    double* dc = static_cast<double*>(ctx->dc.ptr);
+    cudaStream_t st = ctx->stream();
+    std::vector<double> guess(static_cast<size_t>(nm) * 4, 0.0);
+    for (int i = 0; i < nm; ++i) {
+        guess[4 * i] = init_a;
+        guess[4 * i + 1] = std::isnan(init_m) ? m_values[i] : init_m;  // workers.py:167-173: init_m = m_true
+        guess[4 * i + 3] = 0.0;
+    }
+    DFK_CUDA(cudaMemcpyAsync(ctx->qi_seed.ptr, guess.data(), guess.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    DFK_CUDA(cudaStreamSynchronize(st));  // `guess` leaves scope; the copy is 600 bytes
+    for (int i = 0; i < nm; ++i) {
+        rc = dfk_sweep_demod_dev(ctx, ntrials, trial0, R, N, f_samp, f_mod, m_values[i], amp, visibility, phi0, psi0, snr_db,
+                                 seed + static_cast<uint64_t>(i) * static_cast<uint64_t>(seed_stride),
+                                 qi + static_cast<int64_t>(i) * ntrials * 2 * N, dc + static_cast<int64_t>(i) * ntrials);
+        if (rc) return rc;
+    }
+    ProfScope ps(ctx, 1, st);
+    return launch_lm(ctx, qi, nfit, {1, 0, 1}, N, guess_rows(static_cast<const double*>(ctx->qi_seed.ptr), 4, ntrials, false), dc,
+                     opts, rows_dev, st, true);
 }
 
 int dfk_lm_counters_read(dfk_ctx* ctx, dfk_lm_counters* out, int32_t reset) {

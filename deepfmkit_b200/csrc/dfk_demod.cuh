@@ -653,31 +653,11 @@ inline __host__ __device__ PeriodSmem period_smem_layout(int P, int N, int nstag
     return L;
 }
 
-__global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const PeriodParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const PeriodSmem L = period_smem_layout(p.P, p.N, p.nstages);
-    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
-    double* T = reinterpret_cast<double*>(smem_raw + L.off_t);
-    int* row_type = reinterpret_cast<int*>(smem_raw + L.off_rows);
-    int* row_out = row_type + L.nrows;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
-    uint64_t* empty = full + p.nstages;
-    volatile unsigned long long* issued = reinterpret_cast<volatile unsigned long long*>(empty + p.nstages);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int P = p.P, N = p.N, half = P >> 1, quarter = L.quarter, nrows = L.nrows;
-    constexpr int NBW = kPeriodNbw;
-    const long long ngroups = (p.nbuf + NBW - 1) / NBW;
-    const long long my_groups = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
+// Row tables and twiddles of a CTA (all threads call it; it synchronises).
+// row_out: -1 = padding, 0 = mean, k = Q_k (qi column k-1), N + k = I_k (qi column N+k-1).
+DFK_D void period_build_tables(int P, int N, int nrows, int quarter, double* T, int* row_type, int* row_out, int tid,
+                               int nthreads) {
     if (tid == 0) {
-        for (int s = 0; s < p.nstages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        *issued = 0ull;
-        mbar_fence_init();
-        // row tables; row_out: -1 = padding, 0 = mean, k = Q_k (qi column k-1), N + k = I_k (qi column N+k-1)
         int v = 0;
         for (int type = 0; type < 4; ++type) {
             const int k0 = (type == 0) ? 0 : (type == 2 ? 2 : 1);
@@ -698,7 +678,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
         }
     }
     __syncthreads();
-    for (int i = tid; i < (quarter + 1) * nrows; i += kFoldThreads) {
+    for (int i = tid; i < (quarter + 1) * nrows; i += nthreads) {
         const int j = i / nrows, v = i - j * nrows;
         const int out = row_out[v];
         double val = 0.0;
@@ -711,6 +691,117 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
         T[i] = val;
     }
     __syncthreads();
+}
+
+// Combinations of columns j, P-j, j' = P/2-j, P-j' of the nb (<= 8) buffers at sm (buffer s at sm + s*P), written
+// transposed into the warp's scratch X: row j holds AE, AO, BE, BO, eight buffers each.
+DFK_D void period_combos(const double* sm, double* X, int P, int xrow, int nb, int lane) {
+    constexpr int NBW = kPeriodNbw;
+    const int half = P >> 1, quarter = P >> 2;
+    for (int j = lane; j <= quarter; j += 32) {
+        const int jp = half - j;
+        const bool first = j == 0, mid = j == quarter;
+        double2* xr = reinterpret_cast<double2*>(X + j * xrow);
+        double ae[NBW], ao[NBW], be[NBW], bo[NBW];
+#pragma unroll
+        for (int s = 0; s < NBW; ++s) {
+            const bool have = s < nb;
+            const double* row = sm + s * P;
+            const double s1 = have ? row[j] : 0.0;
+            const double s2 = (have && !first) ? row[P - j] : 0.0;
+            const double s3 = have ? row[jp] : 0.0;
+            const double s4 = (have && !first) ? row[half + j] : 0.0;  // column P - j'
+            const double aj = s1 + s2, bj = first ? 0.0 : s1 - s2;
+            const double ap = s3 + s4, bp = first ? 0.0 : s3 - s4;
+            ae[s] = mid ? aj : aj + ap;
+            ao[s] = mid ? 0.0 : aj - ap;
+            be[s] = mid ? 0.0 : bj - bp;
+            bo[s] = mid ? bj : bj + bp;
+        }
+#pragma unroll
+        for (int s = 0; s < NBW; s += 2) {
+            xr[(0 * NBW + s) / 2] = make_double2(ae[s], ae[s + 1]);
+            xr[(1 * NBW + s) / 2] = make_double2(ao[s], ao[s + 1]);
+            xr[(2 * NBW + s) / 2] = make_double2(be[s], be[s + 1]);
+            xr[(3 * NBW + s) / 2] = make_double2(bo[s], bo[s + 1]);
+        }
+    }
+}
+
+// Product of the combinations with the twiddle table: lane -> rows (2i, 2i+1) of each 32-row block, buffers
+// 4h..4h+3 (i = lane % 16, h = lane / 16); results of buffers b0 .. b0+nb-1 to qi / dc.
+DFK_D void period_product(const double* X, const double* T, const int* row_type, const int* row_out, int P, int N, int nrows,
+                          int xrow, int nb, long long b0, double* __restrict__ qi, double* __restrict__ dc, int lane) {
+    constexpr int NBW = kPeriodNbw;
+    const int quarter = P >> 2;
+    const double Rd = static_cast<double>(P);
+    const int pi = lane & 15, h = lane >> 4;
+    for (int vb = 0; vb < nrows; vb += 32) {
+        const int r0 = vb + 2 * pi;
+        const double* tp = T + r0;
+        const double* xp = X + row_type[r0] * NBW + 4 * h;
+        double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int j = 0; j <= quarter; ++j) {
+            const double2 t = *reinterpret_cast<const double2*>(tp + j * nrows);
+            const double2 xa = *reinterpret_cast<const double2*>(xp + j * xrow);
+            const double2 xb = *reinterpret_cast<const double2*>(xp + j * xrow + 2);
+            acc0[0] = fma(t.x, xa.x, acc0[0]);
+            acc0[1] = fma(t.x, xa.y, acc0[1]);
+            acc0[2] = fma(t.x, xb.x, acc0[2]);
+            acc0[3] = fma(t.x, xb.y, acc0[3]);
+            acc1[0] = fma(t.y, xa.x, acc1[0]);
+            acc1[1] = fma(t.y, xa.y, acc1[1]);
+            acc1[2] = fma(t.y, xb.x, acc1[2]);
+            acc1[3] = fma(t.y, xb.y, acc1[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int out = row_out[r0 + r];
+            if (out < 0) continue;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int slot = 4 * h + s;
+                if (slot < nb) {
+                    const double val = (r == 0 ? acc0[s] : acc1[s]) / Rd;
+                    const long long b = b0 + slot;
+                    if (out == 0) {
+                        dc[b] = val;
+                    } else {
+                        qi[b * static_cast<long long>(2 * N) + (out - 1)] = val;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const PeriodParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const PeriodSmem L = period_smem_layout(p.P, p.N, p.nstages);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
+    double* T = reinterpret_cast<double*>(smem_raw + L.off_t);
+    int* row_type = reinterpret_cast<int*>(smem_raw + L.off_rows);
+    int* row_out = row_type + L.nrows;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* empty = full + p.nstages;
+    volatile unsigned long long* issued = reinterpret_cast<volatile unsigned long long*>(empty + p.nstages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, N = p.N, nrows = L.nrows;
+    constexpr int NBW = kPeriodNbw;
+    const long long ngroups = (p.nbuf + NBW - 1) / NBW;
+    const long long my_groups = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        *issued = 0ull;
+        mbar_fence_init();
+    }
+    period_build_tables(P, N, nrows, L.quarter, T, row_type, row_out, tid, kFoldThreads);
 
     if (warp == kFoldConsumerWarps) {
         if (lane == 0) {
@@ -738,8 +829,6 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
     }
 
     double* X = reinterpret_cast<double*>(smem_raw + L.off_x) + warp * L.x_per_warp;
-    const int xrow = L.xrow;
-    const double Rd = static_cast<double>(P);
     for (long long i = warp; i < my_groups; i += kFoldConsumerWarps) {
         const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
         const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
@@ -748,79 +837,10 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
         while (*issued <= static_cast<unsigned long long>(i)) __nanosleep(64);
         __threadfence_block();
         mbar_wait(&full[stage], phase);
-        const double* sm = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
-        // combinations of columns j, P-j, j' = P/2-j, P-j' for the NBW buffers of the group, written transposed
-        for (int j = lane; j <= quarter; j += 32) {
-            const int jp = half - j;
-            const bool first = j == 0, mid = j == quarter;
-            double2* xr = reinterpret_cast<double2*>(X + j * xrow);
-            double ae[NBW], ao[NBW], be[NBW], bo[NBW];
-#pragma unroll
-            for (int s = 0; s < NBW; ++s) {
-                const bool have = s < nb;
-                const double* row = sm + s * P;
-                const double s1 = have ? row[j] : 0.0;
-                const double s2 = (have && !first) ? row[P - j] : 0.0;
-                const double s3 = have ? row[jp] : 0.0;
-                const double s4 = (have && !first) ? row[half + j] : 0.0;  // column P - j'
-                const double aj = s1 + s2, bj = first ? 0.0 : s1 - s2;
-                const double ap = s3 + s4, bp = first ? 0.0 : s3 - s4;
-                ae[s] = mid ? aj : aj + ap;
-                ao[s] = mid ? 0.0 : aj - ap;
-                be[s] = mid ? 0.0 : bj - bp;
-                bo[s] = mid ? bj : bj + bp;
-            }
-#pragma unroll
-            for (int s = 0; s < NBW; s += 2) {
-                xr[(0 * NBW + s) / 2] = make_double2(ae[s], ae[s + 1]);
-                xr[(1 * NBW + s) / 2] = make_double2(ao[s], ao[s + 1]);
-                xr[(2 * NBW + s) / 2] = make_double2(be[s], be[s + 1]);
-                xr[(3 * NBW + s) / 2] = make_double2(bo[s], bo[s + 1]);
-            }
-        }
+        period_combos(stage_base + static_cast<size_t>(stage) * L.stage_doubles, X, P, L.xrow, nb, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-
-        // product: lane -> rows (2i, 2i+1) of the 32-row block, buffers 4h..4h+3   (i = lane % 16, h = lane / 16)
-        const int pi = lane & 15, h = lane >> 4;
-        for (int vb = 0; vb < nrows; vb += 32) {
-            const int r0 = vb + 2 * pi;
-            const double* tp = T + r0;
-            const double* xp = X + row_type[r0] * NBW + 4 * h;
-            double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-            for (int j = 0; j <= quarter; ++j) {
-                const double2 t = *reinterpret_cast<const double2*>(tp + j * nrows);
-                const double2 xa = *reinterpret_cast<const double2*>(xp + j * xrow);
-                const double2 xb = *reinterpret_cast<const double2*>(xp + j * xrow + 2);
-                acc0[0] = fma(t.x, xa.x, acc0[0]);
-                acc0[1] = fma(t.x, xa.y, acc0[1]);
-                acc0[2] = fma(t.x, xb.x, acc0[2]);
-                acc0[3] = fma(t.x, xb.y, acc0[3]);
-                acc1[0] = fma(t.y, xa.x, acc1[0]);
-                acc1[1] = fma(t.y, xa.y, acc1[1]);
-                acc1[2] = fma(t.y, xb.x, acc1[2]);
-                acc1[3] = fma(t.y, xb.y, acc1[3]);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int out = row_out[r0 + r];
-                if (out < 0) continue;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const int slot = 4 * h + s;
-                    if (slot < nb) {
-                        const double val = (r == 0 ? acc0[s] : acc1[s]) / Rd;
-                        const long long b = b0 + slot;
-                        if (out == 0) {
-                            p.dc[b] = val;
-                        } else {
-                            p.qi[b * static_cast<long long>(2 * N) + (out - 1)] = val;
-                        }
-                    }
-                }
-            }
-        }
+        period_product(X, T, row_type, row_out, P, N, nrows, L.xrow, nb, b0, p.qi, p.dc, lane);
         __syncwarp();
     }
 }

@@ -39,7 +39,7 @@ int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, i
 }
 
 int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints, int64_t ntrials, int32_t ncols,
-                        int64_t col_stride, double* out_dev) {
+                        int64_t col_stride, const double* center_dev, double* out_dev) {
     DFK_ENTER(ctx);
     if (npoints < 0 || ntrials < 1 || ncols < 1 || col_stride < ncols)
         return fail(DFK_ERR_ARG, "bad geometry: npoints=%lld ntrials=%lld ncols=%d stride=%lld", (long long)npoints,
@@ -49,7 +49,7 @@ int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints,
     if (npoints * ncols > 0x7fffffffll) return fail(DFK_ERR_ARG, "too many grid points for one launch");
     static_assert(sizeof(dfk::TrialStats) == DFK_TRIAL_STATS_DOUBLES * sizeof(double), "ABI: statistics record size");
     dfk::trial_stats_kernel<<<static_cast<unsigned>(npoints * ncols), dfk::kStatThreads, 0, ctx->stream()>>>(
-        values_dev, npoints, ntrials, ncols, col_stride, reinterpret_cast<dfk::TrialStats*>(out_dev));
+        values_dev, npoints, ntrials, ncols, col_stride, center_dev, reinterpret_cast<dfk::TrialStats*>(out_dev));
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;

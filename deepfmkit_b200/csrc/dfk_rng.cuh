@@ -18,6 +18,19 @@ DFK_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Two standard normals from two 32-bit draws (Box-Muller).  The hardware approximations (lg2.approx, sin/cos.approx on
+// an angle in [-pi, pi): absolute error ~2^-21) are six digits below the draw itself and leave no branch in the
+// generator's inner loop; the radius is exact to fp32 rounding.
+DFK_D void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+    const float ang = (static_cast<float>(b) * 2.3283064365386963e-10f - 0.5f) * 6.283185307179586f;  // [-pi, pi]
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cn;
+    __sincosf(ang, &sn, &cn);
+    z0 = rad * cn;
+    z1 = rad * sn;
+}
+
 // Four standard normals from one Philox block (key, counter): two Box-Muller pairs in fp32.  The noise these feed
 // is 20..60 dB below the signal, so 2^-24 granularity is seven digits below anything a fit can see; |z| <= 6.66.
 DFK_D void normal4(unsigned long long key, unsigned long long counter, uint32_t stream, float z[4]) {
@@ -26,13 +39,7 @@ DFK_D void normal4(unsigned long long key, unsigned long long counter, uint32_t 
                   static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), r);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float u1 = (static_cast<float>(r[2 * h]) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
-        const float u2 = static_cast<float>(r[2 * h + 1]) * 2.3283064365386963e-10f;       // [0, 1]
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float sn, cn;
-        sincospif(2.0f * u2, &sn, &cn);
-        z[2 * h] = rad * cn;
-        z[2 * h + 1] = rad * sn;
+        box_muller(r[2 * h], r[2 * h + 1], z[2 * h], z[2 * h + 1]);
     }
 }
 

@@ -55,8 +55,9 @@ DFK_D double synth_clean(const SynthParams& p, double phi, long long t) {
     return p.amp * (1.0 + p.vis * cos(phi + p.m * th));
 }
 
-DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
-                      long long q) {
+// The four samples t = 4q .. 4q+3 of channel c.
+DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
+                             long long q, double y[4]) {
     const unsigned long long key = p.seed + static_cast<unsigned long long>(c);
     uint32_t r[4];
     philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), 0x5eedu, 0u, static_cast<uint32_t>(key),
@@ -64,16 +65,9 @@ DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, 
     float z[4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float u1 = (static_cast<float>(r[2 * h]) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
-        const float u2 = static_cast<float>(r[2 * h + 1]) * 2.3283064365386963e-10f;       // [0, 1]
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float sn, cn;
-        sincospif(2.0f * u2, &sn, &cn);
-        z[2 * h] = rad * cn;
-        z[2 * h + 1] = rad * sn;
+        box_muller(r[2 * h], r[2 * h + 1], z[2 * h], z[2 * h + 1]);
     }
     const long long t4 = q << 2;
-    double y[4];
     int jm = table ? static_cast<int>(t4 % p.P) : 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -86,6 +80,13 @@ DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, 
         }
         y[e] = fma(sigma, static_cast<double>(z[e]), clean);
     }
+}
+
+DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
+                      long long q) {
+    double y[4];
+    synth_quad_values(p, table, clean_tab, phi, sigma, c, q, y);
+    const long long t4 = q << 2;
     double* dst = p.x + c * p.ld_c - p.t0 + t4;  // indexed by absolute t
     if (t4 >= p.t0 && t4 + 4 <= p.t0 + p.T && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         reinterpret_cast<double2*>(dst)[0] = make_double2(y[0], y[1]);

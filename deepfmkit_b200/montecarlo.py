@@ -6,10 +6,10 @@ one buffer in 'snr' mode with ``trial_num`` as the noise seed and fits it with `
 ``multiprocessing.Pool`` and reduces each grid point to mean / std / min / max / worst-case.  Notebook
 ``1.1_CRLB-test`` (cells 3-6) compares Var(m_hat) with ``calculate_crlb_for_m`` (helpers.py:16-45).
 
-Here the whole grid is one pass: every realisation is generated in HBM by the counter-based 'snr' generator
-(``dfk_synth_snr_dev`` -- statistically, not bitwise, the reference's MT19937 noise), demodulated and fitted by
-``dfk_nls_fit_batch_dev`` with a per-realisation cold start, and reduced on the device.  Waves bound the
-resident record (default 8 GB).
+Here the whole grid is one pass (``dfk_nls_sweep_dev``): every realisation is drawn by the counter-based 'snr' generator
+(statistically, not bitwise, the reference's MT19937 noise) inside the demodulation kernel's shared memory -- no record
+ever touches HBM; the samples are bit for bit those ``dfk_synth_snr_slab_dev`` writes for the same seed -- fitted cold
+in one launch, and reduced on the device.  Waves bound the resident harmonic vectors and rows (default 8 GB).
 """
 from __future__ import annotations
 
@@ -89,51 +89,58 @@ def nls_sweep(m_values, n_trials, snr_db=40.0, f_samp=200e3, f_mod=1000.0, n=1, 
     R = int(f_samp / f_mod * n)
     w0 = 2.0 * np.pi * f_mod / f_samp
     opts = fit_tunables.current_lm_opts(tunables_from)
-    per_wave = max(1, min(int(n_trials), int(max_resident_bytes // (len(ms) * R * 8))))
+    # no record is ever resident: a wave holds harmonic vectors, means and result rows only
+    per_fit = 8 * (2 * int(ndata) + 1) + 8 * _lib.ROW_STRIDE + 16
+    per_wave = max(1, min(int(n_trials), int(max_resident_bytes // (len(ms) * per_fit))))
     seed_stride = int(n_trials) if _seed_stride is None else int(_seed_stride)
-    stats = {k: [] for k in ("sum", "sumsq", "min", "max", "worst", "ok", "ssq")}
+    waves = []
     all_rows = [] if return_rows else None
     with torch.cuda.device(dev):
-        x = torch.empty((len(ms), per_wave, R), dtype=torch.float64, device=dev)
         rows = torch.empty((len(ms), per_wave, _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
-        guess = torch.zeros((len(ms), per_wave, 4), dtype=torch.float64, device=dev)
-        guess[:, :, 0] = init_a
-        guess[:, :, 1] = torch.from_numpy(ms if init_m is None else np.full_like(ms, float(init_m))).to(dev)[:, None]
         truth = torch.from_numpy(np.stack([np.full_like(ms, amp), ms, np.full_like(ms, phi0), np.full_like(ms, psi0)], 1)).to(dev)
+        center = torch.zeros((len(ms), 7), dtype=torch.float64, device=dev)
+        center[:, :4] = truth
         ctx.use_torch_stream()
         try:
             done = 0
             while done < n_trials:
                 nw = min(per_wave, n_trials - done)
-                for i, m in enumerate(ms):  # one generator launch per grid point: realisation = "channel" = seed
-                    ctx.synth_snr_slab_dev(x[i].data_ptr(), R, nw, R, 0, f_samp, f_mod, float(m), amp, visibility, phi0,
-                                           0.0, psi0, snr_db, seed + done + i * seed_stride)
-                xv, rv, gv = x[:, :nw], rows[:, :nw], guess[:, :nw]
-                if nw != per_wave:
-                    xv, rv, gv = xv.contiguous(), rv.contiguous(), gv.contiguous()
-                ctx.nls_fit_batch_dev(xv.data_ptr(), len(ms) * nw, 1, R, R, int(ndata), w0, None, gv.data_ptr(), 4, False,
-                                      opts, rv.data_ptr())
-                p = rv[:, :, :4]
-                stats["sum"].append(p.sum(1))
-                stats["sumsq"].append(((p - truth[:, None, :]) ** 2).sum(1))
-                stats["min"].append(p.min(1).values)
-                stats["max"].append(p.max(1).values)
-                stats["worst"].append((p - truth[:, None, :]).abs().max(1).values)
-                stats["ok"].append(torch.stack([(rv[:, :, 6] == s).sum(1) for s in (0, 1, 2)], 1))
-                stats["ssq"].append(rv[:, :, 5].sum(1))
+                rv = rows[:, :nw] if nw == per_wave else torch.empty((len(ms), nw, _lib.ROW_STRIDE), dtype=torch.float64,
+                                                                      device=dev)
+                # realisation t of grid point i is noise stream seed + i * seed_stride + t, whatever the wave it falls
+                # in: generated inside the demodulation kernel (dfk_nls_sweep_dev), fitted cold in one launch
+                ctx.nls_sweep_dev(ms, nw, done, seed_stride, R, int(ndata), f_samp, f_mod, rv.data_ptr(), amp=amp,
+                                  visibility=visibility, phi0=phi0, psi0=psi0, snr_db=snr_db, seed=seed, init_a=init_a,
+                                  init_m=init_m, opts=opts)
+                # per-m statistics of the wave in one pass of the reduction kernel: columns amp, m, phi, psi, (dc,) ssq,
+                # fitok; "worst" measured from the true parameters
+                st = torch.empty((len(ms), 7, _lib.TRIAL_STATS_DOUBLES), dtype=torch.float64, device=dev)
+                ctx.trial_stats_dev(rv.data_ptr(), len(ms), nw, 7, _lib.ROW_STRIDE, st.data_ptr(), center_ptr=center.data_ptr())
+                waves.append((nw, st))
                 if return_rows:
                     all_rows.append(rv.cpu().numpy().copy())
                 done += nw
             torch.cuda.current_stream(dev).synchronize()
         finally:
             ctx.use_default_stream()
-    part = {"n": int(n_trials), "truth": truth.cpu().numpy(),
-            "sum": torch.stack(stats["sum"]).sum(0).cpu().numpy(), "sumsq": torch.stack(stats["sumsq"]).sum(0).cpu().numpy(),
-            "min": torch.stack(stats["min"]).min(0).values.cpu().numpy(),
-            "max": torch.stack(stats["max"]).max(0).values.cpu().numpy(),
-            "worst": torch.stack(stats["worst"]).max(0).values.cpu().numpy(),
-            "ok": torch.stack(stats["ok"]).sum(0).cpu().numpy().astype(np.float64),
-            "ssq": torch.stack(stats["ssq"]).sum(0).cpu().numpy()}
+    tr = truth.cpu().numpy()
+    part = {"n": int(n_trials), "truth": tr, "sum": 0.0, "sumsq": 0.0, "ok": 0.0, "ssq": 0.0,
+            "min": np.full((len(ms), 4), np.inf), "max": np.full((len(ms), 4), -np.inf), "worst": np.zeros((len(ms), 4))}
+    for nw, st in waves:
+        s_ = st.cpu().numpy()
+        mean, std = s_[:, :4, 0], s_[:, :4, 1]
+        part["sum"] = part["sum"] + mean * nw
+        part["sumsq"] = part["sumsq"] + nw * (std ** 2 + (mean - tr) ** 2)  # about the truth
+        part["min"] = np.minimum(part["min"], s_[:, :4, 2])
+        part["max"] = np.maximum(part["max"], s_[:, :4, 3])
+        part["worst"] = np.maximum(part["worst"], np.abs(s_[:, :4, 4] - tr))
+        part["ssq"] = part["ssq"] + s_[:, 5, 0] * nw
+        # fitok takes the values 0, 1, 2: its first two moments give the three counts
+        f1 = s_[:, 6, 0] * nw
+        f2 = (s_[:, 6, 1] ** 2 + s_[:, 6, 0] ** 2) * nw
+        n2 = np.rint((f2 - f1) / 2.0)
+        n1 = np.rint(f1 - 2.0 * n2)
+        part["ok"] = part["ok"] + np.stack([nw - n1 - n2, n1, n2], 1)
     if _raw_stats:
         return part
     out = _combine_partials(ms, [part], ndata, snr_db, R)

@@ -205,6 +205,24 @@ int dfk_synth_snr_slab_dev(dfk_ctx* ctx, double* x_dev, int64_t T, int64_t C, in
                            double f_mod, double m, double amp, double visibility, double phi0, double dphi,
                            double psi0, double snr_db, uint64_t seed);
 
+/* Monte-Carlo sweep without records: realisations c0 .. c0+nbuf-1 of one grid point -- single 'snr'-mode records of R
+ * samples, noise keyed by seed + index exactly as dfk_synth_snr_slab_dev keys channels -- are generated inside the
+ * demodulation kernel's shared memory and reduced to their harmonic vectors qi_dev[nbuf x 2N] and means dc_dev[nbuf]
+ * (run_efficiency_trial's simulate step, workers.py:132-189, fused with calculate_quadratures).  Bit-identical to
+ * dfk_synth_snr_slab_dev followed by dfk_demod.  One period per record (R = f_samp / f_mod, a multiple of 4, <= 256)
+ * takes the fused kernel; any other geometry generates into scratch and demodulates from there. */
+int dfk_sweep_demod_dev(dfk_ctx* ctx, int64_t nbuf, int64_t c0, int64_t R, int32_t N, double f_samp, double f_mod, double m,
+                        double amp, double visibility, double phi0, double psi0, double snr_db, uint64_t seed,
+                        double* qi_dev, double* dc_dev);
+/* The whole study of notebook 1.1_CRLB-test / BASELINE config 5 in one call: for every m_values[i] (host array),
+ * ntrials realisations (indices trial0 .. trial0+ntrials-1, noise key seed + i * seed_stride + index) generated,
+ * demodulated and fitted cold from [init_a, init_m, 0, 0] -- init_m = NaN starts every fit at its true m
+ * (workers.py:167-173).  rows_dev: nm x ntrials x DFK_ROW_STRIDE. */
+int dfk_nls_sweep_dev(dfk_ctx* ctx, const double* m_values, int32_t nm, int64_t ntrials, int64_t trial0, int64_t seed_stride,
+                      int64_t R, int32_t N, double f_samp, double f_mod, double amp, double visibility, double phi0,
+                      double psi0, double snr_db, uint64_t seed, double init_a, double init_m, const dfk_lm_opts* opts,
+                      double* rows_dev);
+
 /* ---- host-pointer entry points (what the reference-side shim binds) ---------------------- */
 /* StandardNLSFitter.fit on one host record (fitters.py:330-428): nsamp samples, buffers of R,
  * slabs streamed host->device on a copy stream while the previous slab is demodulated and
@@ -278,9 +296,10 @@ int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, i
                       const double* tables_dev, int64_t ntables, double* y_dev, int64_t ld, double* truth_dev);
 /* Per grid point and result column: nanmean, nanstd, nanmin, nanmax, "worst" (the trial farthest from the mean)
  * and the number of finite trials -- the aggregation at the end of Experiment.run (experiments.py:432-446).
- * values_dev[(p * ntrials + t) * col_stride + c]; out_dev[(p * ncols + c) * 6 + {0..5}]. */
+ * values_dev[(p * ntrials + t) * col_stride + c]; out_dev[(p * ncols + c) * 6 + {0..5}].  center_dev (npoints x
+ * ncols, may be NULL): measure "worst" from these values -- e.g. the true parameters -- instead of the mean. */
 int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints, int64_t ntrials, int32_t ncols,
-                        int64_t col_stride, double* out_dev);
+                        int64_t col_stride, const double* center_dev, double* out_dev);
 
 /* ---- post-fit step -------------------------------------------------------------- */
 /* Block means: out[b] = mean(x[b*R .. b*R+R-1]), b < n / R; a tail shorter than R is dropped.

@@ -205,6 +205,16 @@ def test_trial_stats_kernel_matches_numpy(torch_mod):
             if good[p, c]:
                 assert s[p, c, 4] == v[p, np.nanargmax(dev[p, :, c]), c]
                 assert s[p, c, 5] == np.sum(np.isfinite(v[p, :, c]))
+    # "worst" measured from a given centre (the true value in nls_sweep) instead of the mean
+    cen = rng.randn(P, C)
+    ctx.trial_stats_dev(vd.data_ptr(), P, T, C, C, out.data_ptr(), center_ptr=torch_mod.from_numpy(cen).cuda().data_ptr())
+    ctx.synchronize()
+    s2 = out.cpu().numpy()
+    assert np.array_equal(s2[..., :4], s[..., :4], equal_nan=True)
+    for p in range(P):
+        for c in range(C):
+            if good[p, c]:
+                assert s2[p, c, 4] == v[p, np.nanargmax(np.abs(v[p, :, c] - cen[p, c])), c]
 
 
 @pytest.mark.gpu

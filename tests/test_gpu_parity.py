@@ -638,3 +638,22 @@ def test_many_parked_fits_take_the_flat_retry_kernel(torch_mod):
     err = np.abs(got[okr, :4] - ref[okr, :4])
     err[:, :2] /= np.abs(ref[okr, :2])
     assert err.max() <= PARAM_TOL
+
+
+@pytest.mark.parametrize("R,nh,nbuf,c0", [(200, 15, 1003, 0), (200, 10, 64, 4096), (100, 20, 517, 7), (400, 10, 300, 1), (80, 62, 33, 0)])
+def test_fused_sweep_equals_generate_then_demodulate(torch_mod, ctx, R, nh, nbuf, c0):
+    """dfk_sweep_demod_dev makes the realisations inside the demodulation kernel (one period per record) or through
+    scratch (R = 400 here: two periods): either way bit for bit what dfk_synth_snr_slab_dev + dfk_demod give."""
+    f_samp, f_mod, m, seed = 200e3, 1000.0 if R != 100 and R != 80 else (2000.0 if R == 100 else 2500.0), 7.25, 12345
+    w0 = 2.0 * np.pi * f_mod / f_samp
+    x = torch_mod.empty((nbuf, R), dtype=torch_mod.float64, device="cuda")
+    ctx.synth_snr_slab_dev(x.data_ptr(), R, nbuf, R, 0, f_samp, f_mod, m, phi0=0.3, psi0=0.1, snr_db=35.0, seed=seed + c0)
+    qi0 = torch_mod.empty((nbuf, 2 * nh), dtype=torch_mod.float64, device="cuda")
+    dc0 = torch_mod.empty(nbuf, dtype=torch_mod.float64, device="cuda")
+    ctx.demod(x.data_ptr(), nbuf, R, nh, w0, qi0.data_ptr(), dc0.data_ptr())
+    qi1 = torch_mod.full((nbuf, 2 * nh), float("nan"), dtype=torch_mod.float64, device="cuda")
+    dc1 = torch_mod.full((nbuf,), float("nan"), dtype=torch_mod.float64, device="cuda")
+    ctx.sweep_demod_dev(nbuf, c0, R, nh, f_samp, f_mod, m, qi1.data_ptr(), dc1.data_ptr(), phi0=0.3, psi0=0.1, snr_db=35.0,
+                        seed=seed)
+    ctx.synchronize()
+    assert torch_mod.equal(qi0, qi1) and torch_mod.equal(dc0, dc1)
