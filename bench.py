@@ -491,10 +491,129 @@ def other_configs(torch, ctx, stream, clocks, peak, fp64_peak, with_cpu):
                              fp64_peak, m_list=ms,
                              note="cfg5 CRLB Monte Carlo: 1e6 realisations x 19 m in 2..20, one period (200 samples) each, "
                                   "ndata = 15, cold start at m_true = 1.9e7 single-buffer fits, 30.4 GB")
+    out["cfg5"]["monte_carlo_driver"] = sweep_config(torch, ctx, ms, 1_000_000)
     if with_cpu:
         cores = host_cores()
         for name in out:
             out[name]["cpu_baseline"] = cpu_baseline_for(name, cores)
+    return out
+
+
+def sweep_config(torch, ctx, ms, n_trials):
+    """The same study through the Monte-Carlo driver (deepfmkit_b200.nls_sweep): realisations generated inside the
+    demodulation kernel, one cold fit launch, per-m statistics on the device -- generation INCLUDED, nothing resident
+    but harmonic vectors and rows."""
+    from deepfmkit_b200 import _lib, nls_sweep
+    hctx = _lib.get_context(torch.cuda.current_device())
+    nls_sweep(ms, n_trials // 10, seed=1)  # warm-up
+    best, prof = 1e30, None
+    for rep in range(3):
+        hctx.profile_enable(True)
+        hctx.profile_read(reset=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = nls_sweep(ms, n_trials, snr_db=40.0, ndata=15, seed=rep, max_resident_bytes=16 << 30)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        p_ = hctx.profile_read(reset=True)
+        hctx.profile_enable(False)
+        if dt < best:
+            best, prof = dt, p_
+    fits = n_trials * len(ms)
+    return {"value": fits / best, "unit": "fits/s", "wall_ms": best * 1e3, "fits": fits,
+            "generate_and_demodulate_ms": prof["demod_ms"], "lm_ms": prof["lm_ms"],
+            "fitok0_min": float(out["fitok"][:, 0].min()),
+            "std_over_crlb_mean": float((out["m_std"] / out["crlb_sigma_m"]).mean()),
+            "api": "deepfmkit_b200.nls_sweep(range(2, 21), 1e6, ndata=15): host wall clock incl. generation, fits, statistics"}
+
+
+# ---- GPU arm: ingest and post-fit steps around the readout (SURVEY 8f-2, 8f-4) ---------------------------------
+def ingest_and_post(torch, ctx, stream, x, rows, nbuf, w0, opts, local):
+    """(a) the record as 16-bit ADC counts in host memory -> widened on the device -> fitted where it lies;
+    (b) a DFMSWPM text file parsed on the device; (c) block means of the resident record and the LPSD of the fitted
+    phase.  Host wall clock, rank 0, one GPU."""
+    import numpy as np
+    import tempfile
+    from deepfmkit_b200 import StandardNLSFitter, _lib, load_binary, load_raw_device, lpsd, vectorized_downsample
+    out = {}
+    hctx = _lib.get_context(local)
+    n = nbuf * R
+    # (c) post-fit: boxcar of the raw-rate record to the fit rate, LPSD of phi (180 000 points, the reference's defaults)
+    y = vectorized_downsample(x, R)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    y = vectorized_downsample(x, R)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["downsample"] = {"GBps": n * 8 / dt / 1e9, "ms": dt * 1e3, "samples": n, "R": R,
+                         "api": "vectorized_downsample(record, R) on the resident record (dsp.py:3-56)"}
+    del y
+    phi = rows[:, 2].contiguous()
+    lpsd(phi, F_MOD / N_CYCLES)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = lpsd(phi, F_MOD / N_CYCLES, return_type="dict")
+    dt = time.perf_counter() - t0
+    out["lpsd"] = {"ms": dt * 1e3, "points": int(phi.shape[0]), "frequencies": int(len(res["f"])),
+                   "api": "lpsd(fit.phi, fs) with DeepFitObject's defaults: Kaiser 200 dB, Jdes 500, Kdes 100 (core.py:590-609)"}
+    # (a) 16-bit acquisition format: a quarter of the fp64 bytes cross PCIe
+    scale = 2.5 / 32768.0
+    host = np.empty(n, dtype=np.int16)
+    chunk = 1 << 27
+    for off in range(0, n, chunk):  # quantise chunk by chunk: no record-sized temporaries
+        host[off:off + chunk] = torch.clamp(torch.round(x[off:off + chunk] / scale), -32768, 32767).to(torch.int16).cpu().numpy()
+    fitter = StandardNLSFitter({"n": N_CYCLES, "ndata": NDATA})
+
+    def go():
+        raw = load_binary(host, F_SAMP, F_MOD, time_major=True, scale=scale, device=local)[0]
+        return fitter.fit(raw)
+    df = go()
+    t0 = time.perf_counter()
+    df = go()
+    dt = time.perf_counter() - t0
+    got = df.to_numpy(dtype=float)
+    assert got.shape[0] == nbuf and np.all(got[:, 6] == 0) and abs(got[:, 1].mean() - M_TRUE) < 1e-2
+    out["int16_record"] = {"value": nbuf / dt, "unit": UNIT, "ms": dt * 1e3, "h2d_bytes": n * 2, "h2d_GBps": n * 2 / dt / 1e9,
+                           "api": "load_binary(int16 counts in pageable host memory) -> StandardNLSFitter.fit on the "
+                                  "device-resident record -> result frame"}
+    del host
+    # (b) text: 1e6 rows x 2 channels of repr() floats written 12 times over (~470 MB) to a temporary file
+    block_rows, reps = 1_000_000, 12
+    vals = x[:block_rows * 2].cpu().numpy().reshape(block_rows, 2)
+    block = "".join(f"{a!r} {b!r} \n" for a, b in vals.tolist())
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        path = f.name
+        f.write("% raw_data\n% bench\n% Number of channels: 2\n% Start time: 0\n% Sampling frequency: 1000000.0\n"
+                "% Modulation frequency: 1000.0\n%\n%\n%\n%\n%\n%\nch0 ch1 \n")
+        for _ in range(reps):
+            f.write(block)
+    del block
+    nbytes = os.path.getsize(path)
+    rows_txt = block_rows * reps
+    load_raw_device(path, device=local)  # warm-up: staging buffers, page cache
+    t0 = time.perf_counter()
+    data, hdr = load_raw_device(path, device=local)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # the two device phases on their own: upload + row index, then the parse
+    off = hdr["data_offset"]
+    t1 = time.perf_counter()
+    _, nr = hctx.text_load_file(path, off)
+    t2 = time.perf_counter()
+    hctx.text_parse_dev(2, data.data_ptr(), nr)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    hctx.text_release()
+    got = data[:, :1000].cpu().numpy()
+    ok = bool(nr == rows_txt and hdr["nbad"] == 0 and np.allclose(got, vals[:1000].T, rtol=1e-11, atol=0)
+              and np.array_equal(got, data[:, block_rows:block_rows + 1000].cpu().numpy()))
+    os.unlink(path)
+    out["text_file"] = {"GBps_text": nbytes / dt / 1e9, "samples_per_sec": rows_txt * 2 / dt, "ms": dt * 1e3, "bytes": nbytes,
+                        "rows": rows_txt, "channels": 2, "matches_input": ok,
+                        "file_to_hbm_and_row_index_ms": (t2 - t1) * 1e3, "parse_kernels_ms": (t3 - t2) * 1e3,
+                        "parse_kernels_GBps_text": nbytes / (t3 - t2) / 1e9,
+                        "api": "load_raw_device(DFMSWPM raw_data text file): file -> pinned stagers -> HBM -> device parser "
+                               "(bit-identical to the reference's pandas.read_csv); page cache warm"}
     return out
 
 
@@ -692,7 +811,9 @@ def run_gpu(args):
     pinned_s = max_over_ranks(pinned_local)
     del xh
 
-    configs = strong = None
+    configs = strong = around = None
+    if world == 1 and not args.no_configs:
+        around = ingest_and_post(torch, ctx, stream, x, rows, NBUF, w0, opts, local)
     if world == 1 and not args.no_configs:
         peak, _ = measured_peak()
         del x, rows
@@ -736,6 +857,8 @@ def run_gpu(args):
                                      "api": "dfk_nls_fit_host on a pinned host record, rows into pinned memory"}},
             "gpu_launches": launches,
         }
+        if around is not None:
+            line["ingest_and_post"] = around
         if configs is not None:
             line["configs"] = configs
         if strong is not None:

@@ -256,7 +256,45 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
     }
     if (tiled) {
         // launched above
-    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && fold_geometry(ctx, pl, N, leave_room, &g)) {
+    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && pl.P > dfk::kFoldRegisterPeriod &&
+               !dev_int("DFK_NO_FOLD_LONG", 0)) {
+        // fold lengths beyond the register kernel: column chunks of 2048, 32 kB stages (two period slices), as deep
+        // a ring as one CTA per SM holds
+        dfk::FoldParams p;
+        p.x = x;
+        p.qi = qi;
+        p.dc = dc;
+        p.nbuf = nbuf;
+        p.bpc = bpc;
+        p.ld_c = ld_c;
+        p.R = static_cast<int>(R);
+        p.P = static_cast<int>(pl.P);
+        p.periods = static_cast<int>(pl.periods);
+        p.N = N;
+        p.kmul = pl.kmul;
+        p.pps = static_cast<int>(std::min<int64_t>(2, pl.periods));
+        for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];
+        const size_t room = leave_room ? seed_fit_reserve(N) : 0;
+        int nst = 6;
+        size_t smem = 0;
+        for (; nst >= 2; --nst) {
+            smem = dfk::fold_long_smem_layout(p.pps, nst, N, pl.drift).total;
+            if (smem <= static_cast<size_t>(ctx->max_smem_optin) - room) break;
+        }
+        if (nst < 2) return fail(DFK_ERR_ARG, "no shared memory for the long-period demodulation");
+        p.nstages = nst;
+        const int grid = static_cast<int>(std::min<int64_t>(nbuf, ctx->sm_count));
+        if (pl.drift) {
+            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+            dfk::demod_fold_long_kernel<true><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+        } else {
+            DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+            dfk::demod_fold_long_kernel<false><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+        }
+    } else if (pl.folded && aligned && R <= std::numeric_limits<int>::max() && pl.P <= dfk::kFoldRegisterPeriod &&
+               fold_geometry(ctx, pl, N, leave_room, &g)) {
         dfk::FoldParams p;
         p.x = x;
         p.qi = qi;

@@ -284,6 +284,257 @@ __global__ void __launch_bounds__(kFoldThreads, 2) demod_fold_kernel(const FoldP
 }
 
 // ---------------------------------------------------------------------------------------------------
+// demod_fold_long_kernel -- fold lengths beyond the register kernel's 2048 samples (e.g. 10 MHz / 1 kHz = 10 000).
+// The period is cut into column chunks of kLongChunk samples.  For a chunk, the producer streams that chunk's slice
+// of every period of the buffer (rows P samples apart in HBM, one bulk copy each), the consumers fold it in
+// registers exactly as demod_fold_kernel does, park the folded slice in shared memory and project it on the
+// harmonics -- warp k % 8 owns harmonics k and k + 8, lanes stride the slice by 32 columns with a rotation
+// recurrence started from an exact sincospi per chunk -- accumulating over the chunks in registers.  No j <-> P - j
+// pairing (the partners live in different chunks), so the projection covers the whole period: still a small
+// fraction of the fold's time.  Every sample is read from HBM once: the same 8 B/sample roofline.
+constexpr int kLongChunk = 4 * 2 * kFoldConsumers;  // 2048 columns: four column pairs per consumer thread
+constexpr int kLongPasses = (kMaxHarmonics + 2 * kFoldConsumerWarps) / (2 * kFoldConsumerWarps);  // 5: harmonics 0..64, two per warp and pass
+
+struct FoldLongSmem {
+    int stage_doubles;  // pps * kLongChunk
+    size_t off_stage, off_s, off_u, off_step, off_bar, total;
+};
+
+inline __host__ __device__ FoldLongSmem fold_long_smem_layout(int pps, int nstages, int N, bool drift) {
+    FoldLongSmem L;
+    L.stage_doubles = pps * kLongChunk;
+    size_t o = 0;
+    L.off_stage = o;
+    o += static_cast<size_t>(nstages) * L.stage_doubles * 8;
+    L.off_s = o;
+    o += static_cast<size_t>(kLongChunk) * 8;
+    L.off_u = o;
+    o += drift ? static_cast<size_t>(kLongChunk) * 8 : 0;
+    L.off_step = o;
+    o += static_cast<size_t>(N + 1) * 16;
+    L.off_bar = o;
+    o += static_cast<size_t>(2 * nstages) * 8;
+    L.total = o;
+    return L;
+}
+
+template <bool DRIFT>
+__global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const FoldParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FoldLongSmem L = fold_long_smem_layout(p.pps, p.nstages, p.N, DRIFT);
+    double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
+    double* sm_s = reinterpret_cast<double*>(smem_raw + L.off_s);
+    double* sm_u = reinterpret_cast<double*>(smem_raw + L.off_u);
+    double2* sm_step = reinterpret_cast<double2*>(smem_raw + L.off_step);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.off_bar);
+    uint64_t* empty = full + p.nstages;
+    constexpr int SLOTS = 4;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int P = p.P, N = p.N;
+    const int nchunks = (P + kLongChunk - 1) / kLongChunk;
+    const int stages_per_chunk = (p.periods + p.pps - 1) / p.pps;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFoldConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    for (int k = tid; k <= N; k += kFoldThreads) {  // 32-column step of harmonic k
+        const long long r = (static_cast<long long>(k) * p.kmul * 32) % P;
+        double s, c;
+        sincospi(2.0 * static_cast<double>(r) / static_cast<double>(P), &s, &c);
+        sm_step[k] = make_double2(c, s);
+    }
+    __syncthreads();
+
+    if (warp == kFoldConsumerWarps) {
+        if (lane == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long b = blockIdx.x; b < p.nbuf; b += gridDim.x) {
+                const double* src = p.x + (b / p.bpc) * p.ld_c + (b % p.bpc) * static_cast<long long>(p.R);
+                for (int w = 0; w < nchunks; ++w) {
+                    const int wc = min(kLongChunk, P - w * kLongChunk);  // columns of this chunk (even)
+                    for (int q = 0; q < stages_per_chunk; ++q) {
+                        const int np = min(p.pps, p.periods - q * p.pps);
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(np) * static_cast<uint32_t>(wc) * 8u);
+                        double* dst = stage_base + static_cast<size_t>(stage) * L.stage_doubles;
+                        for (int c = 0; c < np; ++c)
+                            bulk_load(dst + static_cast<size_t>(c) * wc,
+                                      src + static_cast<size_t>(q * p.pps + c) * P + static_cast<size_t>(w) * kLongChunk,
+                                      static_cast<uint32_t>(wc) * 8u, &full[stage], pol);
+                        if (++stage == p.nstages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    const double Rd = static_cast<double>(p.R);
+    for (long long b = blockIdx.x; b < p.nbuf; b += gridDim.x) {
+        // running harmonic sums of this warp's harmonics (up to four passes of two: N <= 64)
+        double hacc[kLongPasses][2][4];
+#pragma unroll
+        for (int a = 0; a < kLongPasses; ++a)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hacc[a][h][e] = 0.0;
+        for (int w = 0; w < nchunks; ++w) {
+            const int wc = min(kLongChunk, P - w * kLongChunk);
+            const int whalf = wc >> 1;
+            double2 accS[SLOTS], accT[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                accS[s] = make_double2(0.0, 0.0);
+                accT[s] = make_double2(0.0, 0.0);
+            }
+            for (int q = 0; q < stages_per_chunk; ++q) {
+                const int np = min(p.pps, p.periods - q * p.pps);
+                mbar_wait(&full[stage], phase);
+                const double2* row = reinterpret_cast<const double2*>(stage_base + static_cast<size_t>(stage) * L.stage_doubles) + tid;
+                double cg = static_cast<double>(q * p.pps);
+                for (int c = 0; c < np; ++c) {
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) {
+                        if (tid + s * kFoldConsumers < whalf) {
+                            const double2 v = row[s * kFoldConsumers];
+                            accS[s].x += v.x;
+                            accS[s].y += v.y;
+                            if (DRIFT) {
+                                accT[s].x = fma(cg, v.x, accT[s].x);
+                                accT[s].y = fma(cg, v.y, accT[s].y);
+                            }
+                        }
+                    }
+                    row += whalf;
+                    if (DRIFT) cg += 1.0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == p.nstages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            consumer_bar();  // the previous chunk's projection is over
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int pair = tid + s * kFoldConsumers;
+                if (pair < whalf) {
+                    reinterpret_cast<double2*>(sm_s)[pair] = accS[s];
+                    if (DRIFT) {
+                        // U_j = sum_c (j + cP) x[j + cP] = j S_j + P T_j with the global column j
+                        const double j0 = static_cast<double>(w * kLongChunk + 2 * pair);
+                        const double Pd = static_cast<double>(P);
+                        reinterpret_cast<double2*>(sm_u)[pair] =
+                            make_double2(fma(Pd, accT[s].x, j0 * accS[s].x), fma(Pd, accT[s].y, (j0 + 1.0) * accS[s].y));
+                    }
+                }
+            }
+            consumer_bar();
+            int pass = 0;
+            for (int k0 = warp; k0 <= N; k0 += 2 * kFoldConsumerWarps, ++pass) {
+                const int k1 = k0 + kFoldConsumerWarps;
+                const bool two = k1 <= N;
+                const long long col = static_cast<long long>(w) * kLongChunk + lane;
+                double sa, ca, sb = 0.0, cb = 0.0;
+                sincospi(2.0 * static_cast<double>((static_cast<long long>(k0) * p.kmul * col) % P) / static_cast<double>(P), &sa, &ca);
+                if (two)
+                    sincospi(2.0 * static_cast<double>((static_cast<long long>(k1) * p.kmul * col) % P) / static_cast<double>(P), &sb, &cb);
+                const double2 sta = sm_step[k0];
+                const double2 stb = two ? sm_step[k1] : make_double2(1.0, 0.0);
+                double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};  // Q, I, Q drift, I drift
+                for (int j = lane; j < wc; j += 32) {
+                    const double v = sm_s[j];
+                    acc[0][0] = fma(v, ca, acc[0][0]);
+                    acc[0][1] = fma(v, sa, acc[0][1]);
+                    acc[1][0] = fma(v, cb, acc[1][0]);
+                    acc[1][1] = fma(v, sb, acc[1][1]);
+                    if (DRIFT) {
+                        const double u = sm_u[j];
+                        acc[0][2] = fma(u, sa, acc[0][2]);
+                        acc[0][3] = fma(u, ca, acc[0][3]);
+                        acc[1][2] = fma(u, sb, acc[1][2]);
+                        acc[1][3] = fma(u, cb, acc[1][3]);
+                    }
+                    const double cna = ca * sta.x - sa * sta.y;
+                    sa = fma(sa, sta.x, ca * sta.y);
+                    ca = cna;
+                    const double cnb = cb * stb.x - sb * stb.y;
+                    sb = fma(sb, stb.x, cb * stb.y);
+                    cb = cnb;
+                }
+#pragma unroll
+                for (int a = 0; a < kLongPasses; ++a) {
+                    if (a == pass) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) hacc[a][h][e] += acc[h][e];
+                    }
+                }
+            }
+        }
+        int pass = 0;
+        for (int k0 = warp; k0 <= N; k0 += 2 * kFoldConsumerWarps, ++pass) {
+            const int k1 = k0 + kFoldConsumerWarps;
+            const bool two = k1 <= N;
+            double acc[2][4];
+#pragma unroll
+            for (int a = 0; a < kLongPasses; ++a) {
+                if (a == pass) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[h][e] = hacc[a][h][e];
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = h == 0 ? k0 : k1;
+                if (h == 1 && !two) break;
+                double aq = warp_sum(acc[h][0]), ai = 0.0, aqu = 0.0, aiu = 0.0;
+                if (k > 0) {
+                    ai = warp_sum(acc[h][1]);
+                    if (DRIFT) {
+                        aqu = warp_sum(acc[h][2]);
+                        aiu = warp_sum(acc[h][3]);
+                    }
+                }
+                if (lane == 0) {
+                    if (k == 0) {
+                        p.dc[b] = aq / Rd;
+                    } else {
+                        double qv = aq, iv = ai;
+                        if (DRIFT) {
+                            const double d = p.delta[k - 1];
+                            qv = fma(-d, aqu, qv);
+                            iv = fma(d, aiu, iv);
+                        }
+                        double* out = p.qi + b * static_cast<long long>(2 * N);
+                        out[k - 1] = qv / Rd;
+                        out[N + k - 1] = iv / Rd;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // demod_tile_kernel -- short modulation periods (P <= 256: the 200 kHz configs).  A buffer is then small
 // (32 kB at n = 20, 1.6 kB at n = 1) and the per-buffer block barriers of demod_fold_kernel dominate, so here
 // nothing is synchronised across the CTA: the producer lane streams *groups* of NBW consecutive buffers through

@@ -23,7 +23,8 @@
 namespace dfk {
 
 constexpr int kMaxHarmonics = 64;
-constexpr int64_t kMaxFoldPeriod = 2048;  // 256 consumer threads x 4 column pairs
+constexpr int64_t kFoldRegisterPeriod = 2048;  // demod_fold_kernel: 256 consumer threads x 4 column pairs
+constexpr int64_t kMaxFoldPeriod = 1 << 22;    // demod_fold_long_kernel takes longer fold lengths in column chunks
 constexpr double kDriftRamp = 4e-13;
 constexpr int kMaxFoldMul = 16;
 

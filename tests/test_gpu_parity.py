@@ -128,17 +128,21 @@ def test_tile_and_fold_kernels_agree(torch_mod, ctx, golden, name, monkeypatch):
 @pytest.mark.parametrize("P,n,nh", [(2048, 3, 10), (1536, 2, 7), (1000, 1, 64), (6, 50, 2), (2, 40, 1), (256, 5, 31),
                                     (258, 4, 16), (200, 3, 40), (2050, 2, 5), (75, 20, 10),
                                     (100, 1, 10), (256, 1, 31), (4, 1, 1), (8, 1, 3), (200, 1, 40), (202, 1, 10),
-                                    (12, 1, 5), (200, 1, 16), (75, 1, 10), (333, 6, 12), (1001, 2, 9)])
+                                    (12, 1, 5), (200, 1, 16), (75, 1, 10), (333, 6, 12), (1001, 2, 9),
+                                    (4096, 3, 10), (10000, 2, 10), (16384, 2, 20), (2501, 2, 7), (10000, 20, 64),
+                                    (6144, 1, 3), (2052, 5, 64)])
 def test_demod_period_and_harmonic_extremes(torch_mod, ctx, P, n, nh):
-    """Largest folded period (2048), smallest (2), the tile/fold boundary (256/258), N = 1 and N = 64, a table too big
-    for the tile kernel (N = 40 at P = 200), periods the fold cannot take (2050 > max, 75 odd), and one-period
-    buffers (n = 1) through the quarter-wave kernel (P % 4 == 0) or the tile kernel (P = 202)."""
+    """Largest period of the register fold kernel (2048), smallest (2), the tile/fold boundary (256/258), N = 1 and
+    N = 64, a table too big for the tile kernel (N = 40 at P = 200), an odd period in an odd number of periods (75 x 1:
+    no even fold length -> direct kernel), one-period buffers (n = 1) through the quarter-wave kernel (P % 4 == 0) or
+    the tile kernel (P = 202), and fold lengths beyond 2048 through the column-chunked kernel: 2050 and 2052 (a
+    two- and four-column last chunk), 4096, 6144, 10 000 (10 MHz / 1 kHz), 16 384, 5002 (an odd period doubled)."""
     from deepfmkit_b200 import _lib
     f_mod = 1000.0
     f_samp = f_mod * P
     R = P * n
     w0 = orc.rad_per_sample(f_samp, f_mod)
-    folds = (P % 2 == 0 and P <= 2048) or (P % 2 == 1 and n % 2 == 0 and 2 * P <= 2048)
+    folds = P % 2 == 0 or n % 2 == 0
     assert _lib.demod_path(R, w0) == (1 if folds else 0)
     rng = np.random.RandomState(P + n)
     nbuf = 37
