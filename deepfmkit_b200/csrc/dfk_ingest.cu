@@ -325,7 +325,10 @@ int dfk_widen_dev(dfk_ctx* ctx, const void* src_dev, int32_t dtype, int64_t T, i
     if (T == 0 || C == 0) return DFK_OK;
     if (!src_dev || !out_dev) return fail(DFK_ERR_ARG, "null pointer");
     cudaStream_t st = ctx->stream();
-    if (time_major && C > 1) {
+    if (time_major && C > 1 && C <= dfk::kWidenFewMax) {
+        const int grid = static_cast<int>(std::min<int64_t>((T + 255) / 256, static_cast<int64_t>(ctx->sm_count) * 16));
+        dfk::widen_few_channels_kernel<<<grid, 256, 0, st>>>(src_dev, dtype, T, static_cast<int>(C), scale, offset, out_dev, ld_c);
+    } else if (time_major && C > 1) {
         const int64_t tiles = ((T + dfk::kWidenTile - 1) / dfk::kWidenTile) * ((C + dfk::kWidenTile - 1) / dfk::kWidenTile);
         const int grid = static_cast<int>(std::min<int64_t>(tiles, static_cast<int64_t>(ctx->sm_count) * 16));
         dfk::widen_time_major_kernel<<<grid, dfk::kWidenTile * 8, 0, st>>>(src_dev, dtype, T, C, scale, offset, out_dev, ld_c);

@@ -313,6 +313,17 @@ __global__ void __launch_bounds__(256) widen_channel_major_kernel(const void* __
     }
 }
 
+// Few channels (the usual acquisition card: 1..16): a thread takes one time step, reads its C interleaved samples
+// (consecutive threads read consecutive groups: coalesced) and writes each to its channel's row (coalesced per row).
+constexpr int kWidenFewMax = 16;
+__global__ void __launch_bounds__(256) widen_few_channels_kernel(const void* __restrict__ src, int dtype, long long T, int C,
+                                                                double scale, double offset, double* __restrict__ out,
+                                                                long long ld_c) {
+    for (long long t = blockIdx.x * 256ll + threadIdx.x; t < T; t += static_cast<long long>(gridDim.x) * 256ll) {
+        for (int c = 0; c < C; ++c) out[c * ld_c + t] = fma(scale, raw_load_any(src, dtype, t * C + c), offset);
+    }
+}
+
 constexpr int kWidenTile = 32;
 __global__ void __launch_bounds__(kWidenTile* 8) widen_time_major_kernel(const void* __restrict__ src, int dtype, long long T,
                                                                         long long C, double scale, double offset,

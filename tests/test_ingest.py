@@ -204,6 +204,19 @@ def test_binary_ingest(torch_mod, tmp_path, dtype, time_major):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("C", [2, 16, 17, 40])
+def test_widen_channel_counts(torch_mod, C):
+    """Interleaved records of few channels (thread per time step) and of many (shared-memory tile transpose)."""
+    from deepfmkit_b200 import load_binary
+    rng = np.random.RandomState(C)
+    T = 10007
+    a = (rng.randn(T, C) * 3000).astype(np.int16)
+    raws = load_binary(a, 200e3, 1000.0, time_major=True, scale=1e-3, offset=-0.5)
+    got = np.stack([r.device_data.cpu().numpy() for r in raws])
+    assert np.array_equal(got, io_orc.widen(a, T, C, True, 1e-3, -0.5))
+
+
+@pytest.mark.gpu
 def test_facade_load_raw_then_fit(torch_mod, tmp_path):
     """load_raw -> fit on the record where it lies == the fit of the same samples handed over as a pandas frame."""
     from deepfmkit_b200 import DeepFitFramework, DeepRawObject
