@@ -34,11 +34,12 @@ def main():
         assert rows.shape == single.shape == (nbuf, 8)
         # a rank boundary is a chunk boundary of the warm-start chain (the pool schedule at n_cores = world), the
         # one-GPU call below seeds every buffer from buffer 0: the two differ like any two reference schedules do
-        # (<= 1e-10), far inside the 1e-8 gate; flags, dc and the demodulation are schedule-independent
+        # (<= 1e-10), far inside the 1e-8 gate; flags are identical, dc agrees to rounding (the slabs are
+        # demodulated in groups of a different size)
         assert np.array_equal(rows[:, 6], single[:, 6])
         dev = np.max(np.abs(rows[:, :4] - single[:, :4]))
         print(f"sharded vs one-GPU: max |d param| = {dev:.3e}")
-        assert dev < 1e-9 and np.array_equal(rows[:, 4], single[:, 4])
+        assert dev < 1e-9 and np.max(np.abs(rows[:, 4] - single[:, 4])) <= 1e-15 * np.max(np.abs(single[:, 4]))
         assert np.allclose(rows[:, 5], single[:, 5], rtol=1e-6, atol=1e-18)
         ref = orc.nls_fit(x, f_samp, f_mod, n, nh, schedule="gpu")
         assert np.array_equal(rows[:, 6], ref[:, 6])
