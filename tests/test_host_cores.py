@@ -289,7 +289,8 @@ def test_demod_plan_fold_lengths(hh):
     assert plan(3240, 200e3, 1234.5)[0] == 0             # incommensurate
     assert plan(4100, 200e3, 1000.0)[0] == 0             # buffer is not a whole number of periods
     assert plan(75, 30e3, 400.0)[0] == 0                 # one odd period per buffer: no even fold fits
-    assert plan(80000, 4e6, 1000.0)[0] == 0              # 4000 samples per period: longer than the kernels fold
+    assert plan(80000, 4e6, 1000.0) == (1, 4000, 1)      # beyond the register kernel: the column-chunked fold
+    assert plan(200000, 10e6, 1000.0) == (1, 10000, 1)   # 10 MHz / 1 kHz
 
 
 @pytest.mark.parametrize("f_samp,f_mod,n,nh", [(30e3, 400.0, 20, 10), (162.5e3, 1000.0, 20, 8)])
