@@ -80,7 +80,7 @@ def gather_rows(local_rows, n_units: int, dst: int = 0, group=None, return_tenso
 
 
 def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, group=None, tunables_from=None,
-                    chunks_per_rank=1, gather=True, return_tensor=False):
+                    chunks_per_rank=1, gather=True, return_tensor=False, first_buffer=None):
     """NLS readout of one long record sharded over the ranks of ``group`` as contiguous buffer-aligned slabs.
 
     Every rank calls this with *its* slab: ``x_slab`` holds buffers ``slab_bounds(n_buffers_total, world, rank)``
@@ -90,8 +90,10 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
     [amp, m, phi, psi] is broadcast (32 bytes); then all ranks, rank 0 included, fit their slabs concurrently as
     ``chunks_per_rank`` chains started from that seed (fitters.py:407-417 -- a rank boundary is a chunk boundary,
     i.e. the reference's pool schedule with ``n_cores = world * chunks_per_rank``).  No other exchange: the kernels
-    of different ranks never communicate.  Returns the full ``[n_buffers_total, 8]`` row table on rank 0 (None
-    elsewhere), or with ``gather=False`` this rank's own rows.
+    of different ranks never communicate.  ``first_buffer``: the R samples of the record's buffer 0, given to every
+    rank (160 kB for config 2) -- each rank then fits it itself and nothing is exchanged before the slab kernels.
+    Returns the full ``[n_buffers_total, 8]`` row table on rank 0 (None elsewhere), or with ``gather=False`` this rank's
+    own rows.
     """
     import torch
     import torch.distributed as dist
@@ -117,11 +119,19 @@ def nls_fit_sharded(x_slab, n_buffers_total, R, ndata, w0, init, device=None, gr
             ctx.use_torch_stream()
             try:
                 seed_local = np.zeros(4)
-                if rank == 0 and nb > 0:
-                    ctx.nls_fit_dev(xt.data_ptr(), 1, R, ndata, w0, init, _lib.SCHED_EACH, opts, rows.data_ptr())
-                    torch.cuda.current_stream(dev).synchronize()
-                    seed_local = rows[0, :4].cpu().numpy()
-                seed = broadcast_seed(seed_local, src=0, group=group)
+                if first_buffer is not None:  # every rank fits buffer 0 redundantly: no exchange before the kernels
+                    fb = first_buffer if isinstance(first_buffer, torch.Tensor) else torch.from_numpy(
+                        np.ascontiguousarray(first_buffer, dtype=np.float64))
+                    fb = fb.to(dev).contiguous().view(-1)
+                    row0 = rows[:1] if (rank == 0 and nb > 0) else torch.empty((1, _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
+                    ctx.nls_fit_dev(fb.data_ptr(), 1, R, ndata, w0, init, _lib.SCHED_EACH, opts, row0.data_ptr())
+                    seed = row0[0, :4].cpu().numpy()
+                else:
+                    if rank == 0 and nb > 0:
+                        ctx.nls_fit_dev(xt.data_ptr(), 1, R, ndata, w0, init, _lib.SCHED_EACH, opts, rows.data_ptr())
+                        torch.cuda.current_stream(dev).synchronize()
+                        seed_local = rows[0, :4].cpu().numpy()
+                    seed = broadcast_seed(seed_local, src=0, group=group)
                 if nb - first > 0:
                     ctx.nls_fit_seeded_dev(xt.data_ptr() + first * R * 8, nb - first, R, ndata, w0, seed, opts,
                                            rows.data_ptr() + first * _lib.ROW_STRIDE * 8, chunks=chunks_per_rank)

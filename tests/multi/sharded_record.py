@@ -28,6 +28,13 @@ def main():
     w0 = orc.rad_per_sample(f_samp, f_mod)
     lo, hi = slab_bounds(nbuf, world, rank)
     rows = nls_fit_sharded(x[lo * R:hi * R], nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0], device=local)
+    # the same with the slab resident on the device and buffer 0 handed to every rank: no broadcast, same rows
+    rows_fb = nls_fit_sharded(torch.from_numpy(x[lo * R:hi * R].copy()).cuda(), nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0],
+                              device=local, first_buffer=x[:R])
+    rows_bc = nls_fit_sharded(torch.from_numpy(x[lo * R:hi * R].copy()).cuda(), nbuf, R, nh, w0, [1.6, 6.0, 0.0, 0.0],
+                              device=local)
+    if rank == 0:
+        assert np.array_equal(rows_fb, rows_bc)
     if rank == 0:
         ctx = _lib.get_context(local)
         single = ctx.nls_fit_host(x, R, nh, w0, [1.6, 6.0, 0.0, 0.0], seeded=True)
