@@ -15,6 +15,18 @@ import numpy as np
 from .fitters import EKFFitter, StandardNLSFitter
 
 
+def _reference_fitters():
+    """The experimental W-DFMI / HW-DFMI fitters of the reference (scipy-optimiser bound, outside this package), under
+    the method names core.py:452-459 gives them -- available when the reference itself is importable as ``DeepFMKit``."""
+    try:
+        from DeepFMKit import fitters as ref
+    except Exception:
+        return {}
+    names = {"wdfmi_ortho": "WDFMI_OrthogonalFitter", "wdfmi_nls": "WDFMI_NLSFitter", "wdfmi_seq": "WDFMI_SequentialFitter",
+             "hwdfmi": "HWDFMI_Fitter"}
+    return {method: getattr(ref, cls) for method, cls in names.items() if hasattr(ref, cls)}
+
+
 class DeepRawObject:
     """One channel of raw data: what the fitters read (data.py:16-118 holds the full container).
 
@@ -176,6 +188,7 @@ class DeepFitFramework:
 
     def fit(self, main_label, method="nls", fit_label=None, **kwargs):
         fitter_map = {"nls": StandardNLSFitter, "ekf": EKFFitter}
+        fitter_map.update(_reference_fitters())  # the W-DFMI family stays with the reference (core.py:452-459)
         if method not in fitter_map:
             logging.error(f"Unknown fit method: '{method}'. Available: {list(fitter_map.keys())}")
             return
@@ -193,9 +206,21 @@ class DeepFitFramework:
             n_cycles = sim_obj.fit_n if sim_obj else 20
         R, fs, nbuf = self.fit_init(main_label, n_cycles)
 
+        phi_sim = getattr(main_raw, "phi_sim", None)
+        if phi_sim is not None and len(phi_sim) > 0:  # core.py:480-481: ground truth at the fit rate
+            from .spectra import vectorized_downsample
+            main_raw.phi_sim_downsamp = vectorized_downsample(phi_sim, R)
+
         fit_config = {"n": n_cycles}
+        fitter_args = {"main_raw": main_raw}
+        if "wdfmi" in method:  # core.py:492-496 (reference fitters only)
+            witness_label = kwargs.get("witness_label")
+            if not witness_label or witness_label not in self.raws:
+                logging.error(f"W-DFMI method '{method}' requires a valid 'witness_label'.")
+                return
+            fitter_args["witness_raw"] = self.raws[witness_label]
         fitter = FitterClass(fit_config)
-        results_df = fitter.fit(main_raw=main_raw, **kwargs)
+        results_df = fitter.fit(**fitter_args, **kwargs)
         if results_df is None or results_df.empty:
             logging.error(f"{FitterClass.__name__} returned no results.")
             return None

@@ -261,6 +261,8 @@ def test_facade_simulate_then_fit(torch_mod):
     raw = dff.raws["main"]
     assert raw.device_data.is_cuda and len(raw) == 100000 and raw.phi_sim.shape[0] == 100000
     fit = dff.fit("main")  # n from sims['main'].fit_n = 20
+    truth = raw.phi_sim_downsamp  # core.py:480-481: the ground-truth phase brought to the fit rate
+    assert truth.shape[0] == 25 and np.allclose(truth.cpu().numpy(), raw.phi_sim.cpu().numpy().reshape(25, -1).mean(1), rtol=1e-14)
     assert fit.nbuf == 25 and np.all(np.abs(fit.m - 6.0) < 1e-3) and np.allclose(fit.tau, fit.m / (2 * np.pi * laser.df))
     y_ref, _ = orc.asd_signal(6.0, 200e3, 1000.0, 0.5)
     assert np.max(np.abs(raw.data["ch0"].to_numpy() - y_ref)) < REC_TOL
