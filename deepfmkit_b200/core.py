@@ -16,7 +16,7 @@ from .fitters import EKFFitter, StandardNLSFitter
 
 
 def _reference_fitters():
-    """The experimental W-DFMI / HW-DFMI fitters of the reference (scipy-optimiser bound, outside this package), under
+    """The experimental W-DFMI / HW-DFMI fitters of the reference (bound to a general-purpose optimiser, outside this package), under
     the method names core.py:452-459 gives them -- available when the reference itself is importable as ``DeepFMKit``."""
     try:
         from DeepFMKit import fitters as ref
