@@ -155,32 +155,44 @@ int launch_tile_t(dfk_ctx* ctx, const dfk::TileParams& p, size_t smem, int grid,
 }
 
 // One period per buffer (R == P <= 256, P % 4 == 0, no drift term): the quarter-wave kernel.  1 = launched, 0 = does not fit.
+template <int WARPS>
+int launch_period_t(dfk_ctx* ctx, dfk::PeriodParams p, bool leave_room, int64_t ngroups, cudaStream_t st) {
+    int nst = dev_int("DFK_PERIOD_NSTAGES", WARPS);  // a stage per consumer warp: measured flat from 6 stages up
+    size_t smem = 0;
+    for (; nst >= 2; --nst) {
+        smem = dfk::period_smem_layout(p.P, p.N, nst, WARPS).total;
+        if (smem <= static_cast<size_t>(ctx->max_smem_optin) - (leave_room ? seed_fit_reserve(p.N) : 0)) break;
+    }
+    if (nst < 2) return 0;
+    p.nstages = nst;
+    const int grid = static_cast<int>(std::min<int64_t>(ngroups, ctx->sm_count));
+    DFK_CUDA(cudaFuncSetAttribute(dfk::demod_period_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    dfk::demod_period_kernel<WARPS><<<grid, (WARPS + 1) * 32, smem, st>>>(p);
+    return 1;
+}
+
 int try_launch_period(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int64_t nbuf, int32_t N, double* qi,
                       double* dc, bool leave_room, cudaStream_t st) {
     if (pl.periods != 1 || pl.kmul != 1 || pl.drift || pl.P > dfk::kTileMaxPeriod || (pl.P % 4) != 0 || dev_int("DFK_NO_PERIOD", 0))
         return 0;
-    const int P = static_cast<int>(pl.P);
-    int nst = 12;
-    size_t smem = 0;
-    for (; nst >= 2; --nst) {
-        smem = dfk::period_smem_layout(P, N, nst).total;
-        if (smem <= static_cast<size_t>(ctx->max_smem_optin) - (leave_room ? seed_fit_reserve(N) : 0)) break;
-    }
-    if (nst < 2) return 0;
+    if (reinterpret_cast<uintptr_t>(qi) & 15u) return 0;  // the kernel stores harmonic vectors 128 bits at a time
     dfk::PeriodParams p;
     p.x = x;
     p.qi = qi;
     p.dc = dc;
     p.nbuf = nbuf;
-    p.P = P;
+    p.P = static_cast<int>(pl.P);
     p.N = N;
-    p.nstages = nst;
+    p.nstages = 0;
     const int64_t ngroups = (nbuf + dfk::kPeriodNbw - 1) / dfk::kPeriodNbw;
-    const int grid = static_cast<int>(std::min<int64_t>(ngroups, ctx->sm_count));
-    DFK_CUDA(cudaFuncSetAttribute(dfk::demod_period_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    dfk::demod_period_kernel<<<grid, dfk::kFoldThreads, smem, st>>>(p);
-    return 1;
+    // consumer warps against ring depth: each warp's scratch costs one stage's worth of shared memory
+    switch (dev_int("DFK_PERIOD_WARPS", dfk::kPeriodWarps)) {
+        case 6: return launch_period_t<6>(ctx, p, leave_room, ngroups, st);
+        case 10: return launch_period_t<10>(ctx, p, leave_room, ngroups, st);
+        case 12: return launch_period_t<12>(ctx, p, leave_room, ngroups, st);
+        default: return launch_period_t<8>(ctx, p, leave_room, ngroups, st);
+    }
 }
 
 // Short periods (P <= 256) with contiguous buffers: the barrier-free tile kernel.  Returns 1 if it launched,
@@ -1167,7 +1179,8 @@ int dfk_sweep_demod_dev(dfk_ctx* ctx, int64_t nbuf, int64_t c0, int64_t R, int32
     const bool whole = per == std::floor(per) && per >= 1.0;
     const int64_t P = whole ? static_cast<int64_t>(per) : 0;
     // fused path: one whole period per record, the geometry of the quarter-wave kernel, tables that fit the SM
-    if (whole && R == P && P <= dfk::kTileMaxPeriod && (P % 4) == 0 && !dev_int("DFK_NO_SWEEP_FUSE", 0)) {
+    if (whole && R == P && P <= dfk::kTileMaxPeriod && (P % 4) == 0 && (reinterpret_cast<uintptr_t>(qi_dev) & 15u) == 0 &&
+        !dev_int("DFK_NO_SWEEP_FUSE", 0)) {
         const dfk::SweepSmem S = dfk::sweep_smem_layout(static_cast<int>(P), N);
         if (S.total <= static_cast<size_t>(ctx->max_smem_optin)) {
             dfk::SweepParams sp = {};

@@ -857,6 +857,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_tile_kernel(const TileP
 //   * every lane produces 2 output rows x 4 buffers (instead of 1 x 8), which loads 6 operands per 8 FMAs
 //     instead of 9: shared-memory loads are charged per lane-byte, broadcast or not.
 constexpr int kPeriodNbw = 8;
+constexpr int kPeriodWarps = 8;  // default consumer warps of demod_period_kernel<WARPS> (+ one producer warp)
 
 struct PeriodParams {
     const double* x;
@@ -873,15 +874,20 @@ struct PeriodSmem {
     size_t x_per_warp;  // doubles
 };
 
-// output rows in the order cos-even (k = 0, 2, ..), cos-odd, sin-even, sin-odd, each block padded to an even count
-// so that a lane's two rows always read the same operand; total padded to a multiple of 32.
+// output rows in the order cos-even (k = 0, 2, ..), cos-odd, sin-even, sin-odd, each block padded to a multiple of
+// four so that the four rows of a lane always read the same operand; total padded to a multiple of 32.
 inline __host__ __device__ int period_rows(int N) {
     const int ce = N / 2 + 1, co = (N + 1) / 2, se = N / 2, so = (N + 1) / 2;
-    const int tot = (ce + (ce & 1)) + (co + (co & 1)) + (se + (se & 1)) + (so + (so & 1));
+    const int tot = ((ce + 3) & ~3) + ((co + 3) & ~3) + ((se + 3) & ~3) + ((so + 3) & ~3);
     return (tot + 31) / 32 * 32;
 }
 
-inline __host__ __device__ PeriodSmem period_smem_layout(int P, int N, int nstages) {
+// Where row r of the twiddle table sits inside its 32-row block: the block is stored as two halves of eight 16-byte
+// chunks, chunk g of half h holding rows 4g + 2h, 4g + 2h + 1 -- so that the eight row groups of a warp read eight
+// consecutive chunks with each of their two loads.
+inline __host__ __device__ int period_row_slot(int r) { return (r & ~31) + ((r & 3) >> 1) * 16 + ((r >> 2) & 7) * 2 + (r & 1); }
+
+inline __host__ __device__ PeriodSmem period_smem_layout(int P, int N, int nstages, int warps = kPeriodWarps) {
     PeriodSmem L;
     L.quarter = P / 4;
     L.nrows = period_rows(N);
@@ -894,7 +900,7 @@ inline __host__ __device__ PeriodSmem period_smem_layout(int P, int N, int nstag
     L.off_t = o;
     o += static_cast<size_t>(L.quarter + 1) * L.nrows * 8;
     L.off_x = o;
-    o += kFoldConsumerWarps * L.x_per_warp * 8;
+    o += static_cast<size_t>(warps) * L.x_per_warp * 8;
     L.off_rows = o;
     o += static_cast<size_t>(L.nrows) * 2 * sizeof(int);  // row_type[], row_out[]
     o = (o + 7) & ~static_cast<size_t>(7);
@@ -912,15 +918,13 @@ DFK_D void period_build_tables(int P, int N, int nrows, int quarter, double* T, 
         int v = 0;
         for (int type = 0; type < 4; ++type) {
             const int k0 = (type == 0) ? 0 : (type == 2 ? 2 : 1);
-            int cnt = 0;
-            for (int k = k0; k <= N; k += 2, ++cnt, ++v) {
+            for (int k = k0; k <= N; k += 2, ++v) {
                 row_type[v] = type;
                 row_out[v] = type < 2 ? k : N + k;
             }
-            if (cnt & 1) {
+            for (; v & 3; ++v) {
                 row_type[v] = type;
                 row_out[v] = -1;
-                ++v;
             }
         }
         for (; v < nrows; ++v) {
@@ -939,97 +943,129 @@ DFK_D void period_build_tables(int P, int N, int nrows, int quarter, double* T, 
             sincospi(2.0 * static_cast<double>((static_cast<long long>(k) * j) % P) / static_cast<double>(P), &sn, &cs);
             val = out <= N ? cs : sn;
         }
-        T[i] = val;
+        T[j * nrows + period_row_slot(v)] = val;
     }
     __syncthreads();
 }
 
-// Combinations of columns j, P-j, j' = P/2-j, P-j' of the nb (<= 8) buffers at sm (buffer s at sm + s*P), written
-// transposed into the warp's scratch X: row j holds AE, AO, BE, BO, eight buffers each.
-DFK_D void period_combos(const double* sm, double* X, int P, int xrow, int nb, int lane) {
+// Combinations of columns j, P-j, j' = P/2-j, P-j' of the eight buffers at sm (buffer s at sm + s*P), written
+// transposed into the warp's scratch X: row j holds AE, AO, BE, BO, eight buffers each.  Buffers past the end of a
+// ragged last group hold stale bytes; their outputs are never stored, so they are combined like the rest.
+// Interior columns 0 < j < P/4 take the branch-free path; the two self-paired columns j = 0 and j = P/4 follow on two
+// lanes.
+template <bool EDGE>
+DFK_D void period_combo_column(const double* sm, double* X, int P, int xrow, int j) {
     constexpr int NBW = kPeriodNbw;
     const int half = P >> 1, quarter = P >> 2;
-    for (int j = lane; j <= quarter; j += 32) {
-        const int jp = half - j;
-        const bool first = j == 0, mid = j == quarter;
-        double2* xr = reinterpret_cast<double2*>(X + j * xrow);
-        double ae[NBW], ao[NBW], be[NBW], bo[NBW];
+    const int jp = half - j;
+    const bool first = EDGE && j == 0, mid = EDGE && j == quarter;
+    double2* xr = reinterpret_cast<double2*>(X + j * xrow);
+    double ae[NBW], ao[NBW], be[NBW], bo[NBW];
 #pragma unroll
-        for (int s = 0; s < NBW; ++s) {
-            const bool have = s < nb;
-            const double* row = sm + s * P;
-            const double s1 = have ? row[j] : 0.0;
-            const double s2 = (have && !first) ? row[P - j] : 0.0;
-            const double s3 = have ? row[jp] : 0.0;
-            const double s4 = (have && !first) ? row[half + j] : 0.0;  // column P - j'
-            const double aj = s1 + s2, bj = first ? 0.0 : s1 - s2;
-            const double ap = s3 + s4, bp = first ? 0.0 : s3 - s4;
-            ae[s] = mid ? aj : aj + ap;
-            ao[s] = mid ? 0.0 : aj - ap;
-            be[s] = mid ? 0.0 : bj - bp;
-            bo[s] = mid ? bj : bj + bp;
-        }
+    for (int s = 0; s < NBW; ++s) {
+        const double* row = sm + s * P;
+        const double s1 = row[j];
+        const double s2 = first ? 0.0 : row[P - j];
+        const double s3 = row[jp];
+        const double s4 = first ? 0.0 : row[half + j];  // column P - j'
+        const double aj = s1 + s2, bj = first ? 0.0 : s1 - s2;
+        const double ap = s3 + s4, bp = first ? 0.0 : s3 - s4;
+        ae[s] = mid ? aj : aj + ap;
+        ao[s] = mid ? 0.0 : aj - ap;
+        be[s] = mid ? 0.0 : bj - bp;
+        bo[s] = mid ? bj : bj + bp;
+    }
+    // chunk (type, hb, half) = half * 8 + type * 2 + hb holds buffers 4 hb + 2 half, + 1: the product's two loads
+    // per lane (half 0, half 1) each sweep eight consecutive chunks over the (type, hb) pairs of a warp
 #pragma unroll
-        for (int s = 0; s < NBW; s += 2) {
-            xr[(0 * NBW + s) / 2] = make_double2(ae[s], ae[s + 1]);
-            xr[(1 * NBW + s) / 2] = make_double2(ao[s], ao[s + 1]);
-            xr[(2 * NBW + s) / 2] = make_double2(be[s], be[s + 1]);
-            xr[(3 * NBW + s) / 2] = make_double2(bo[s], bo[s + 1]);
-        }
+    for (int s = 0; s < NBW; s += 2) {
+        const int c = ((s >> 1) & 1) * 8 + (s >> 2);
+        xr[c + 0] = make_double2(ae[s], ae[s + 1]);
+        xr[c + 2] = make_double2(ao[s], ao[s + 1]);
+        xr[c + 4] = make_double2(be[s], be[s + 1]);
+        xr[c + 6] = make_double2(bo[s], bo[s + 1]);
     }
 }
 
-// Product of the combinations with the twiddle table: lane -> rows (2i, 2i+1) of each 32-row block, buffers
-// 4h..4h+3 (i = lane % 16, h = lane / 16); results of buffers b0 .. b0+nb-1 to qi / dc.
-DFK_D void period_product(const double* X, const double* T, const int* row_type, const int* row_out, int P, int N, int nrows,
-                          int xrow, int nb, long long b0, double* __restrict__ qi, double* __restrict__ dc, int lane) {
-    constexpr int NBW = kPeriodNbw;
+DFK_D void period_combos(const double* sm, double* X, int P, int xrow, int lane) {
     const int quarter = P >> 2;
-    const double Rd = static_cast<double>(P);
-    const int pi = lane & 15, h = lane >> 4;
+    for (int j = 1 + lane; j < quarter; j += 32) period_combo_column<false>(sm, X, P, xrow, j);
+    if (lane < 2) period_combo_column<true>(sm, X, P, xrow, lane == 0 ? 0 : quarter);
+}
+
+// Product of the combinations with the twiddle table.  Lane = (row group g = lane % 8: rows 4g..4g+3 of each 32-row
+// block, buffer half hb = (lane / 8) % 2: buffers 4hb..4hb+3, column parity = lane / 16): 16 accumulators fed by four
+// 128-bit loads per column -- 4 bytes of shared memory per FMA instead of 6 -- the two half-warps taking alternate
+// columns and adding up at the end.  The results of the group are laid out in the warp's scratch as they lie in
+// memory (qi rows of consecutive buffers are contiguous) and leave with 128-bit stores.
+// out_stage: 8 * 2N + 8 doubles of warp-private shared memory that the product no longer reads (the head of X).
+DFK_D void period_product(double* X, const double* T, const int* row_type, const int* row_out, int P, int N, int nrows,
+                          int xrow, int nb, long long b0, double* __restrict__ qi, double* __restrict__ dc, int lane) {
+    const int quarter = P >> 2;
+    const double inv_r = 1.0 / static_cast<double>(P);
+    const int g = lane & 7, hb = (lane >> 3) & 1, par = lane >> 4;
+    const int two_n = 2 * N;
+    const bool staged = nrows == 32;  // one 32-row block (N <= 15): X is free once its loop ends
     for (int vb = 0; vb < nrows; vb += 32) {
-        const int r0 = vb + 2 * pi;
-        const double* tp = T + r0;
-        const double* xp = X + row_type[r0] * NBW + 4 * h;
-        double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-        for (int j = 0; j <= quarter; ++j) {
-            const double2 t = *reinterpret_cast<const double2*>(tp + j * nrows);
-            const double2 xa = *reinterpret_cast<const double2*>(xp + j * xrow);
-            const double2 xb = *reinterpret_cast<const double2*>(xp + j * xrow + 2);
-            acc0[0] = fma(t.x, xa.x, acc0[0]);
-            acc0[1] = fma(t.x, xa.y, acc0[1]);
-            acc0[2] = fma(t.x, xb.x, acc0[2]);
-            acc0[3] = fma(t.x, xb.y, acc0[3]);
-            acc1[0] = fma(t.y, xa.x, acc1[0]);
-            acc1[1] = fma(t.y, xa.y, acc1[1]);
-            acc1[2] = fma(t.y, xb.x, acc1[2]);
-            acc1[3] = fma(t.y, xb.y, acc1[3]);
-        }
+        const int r0 = vb + 4 * g;
+        const double* tp = T + vb + 2 * g;                     // + 16 for rows 2, 3 of the group
+        const double* xp = X + (row_type[r0] * 2 + hb) * 2;   // + 16 for buffers 2, 3 of the half
+        double acc[4][4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int out = row_out[r0 + r];
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[r][s] = 0.0;
+#pragma unroll 2
+        for (int j = par; j <= quarter; j += 2) {
+            const double2 t01 = *reinterpret_cast<const double2*>(tp + j * nrows);
+            const double2 t23 = *reinterpret_cast<const double2*>(tp + j * nrows + 16);
+            const double2 xa = *reinterpret_cast<const double2*>(xp + j * xrow);
+            const double2 xb = *reinterpret_cast<const double2*>(xp + j * xrow + 16);
+            const double t[4] = {t01.x, t01.y, t23.x, t23.y};
+            const double x[4] = {xa.x, xa.y, xb.x, xb.y};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) acc[r][s] = fma(t[r], x[s], acc[r][s]);
+        }
+        // even + odd columns; the lower half-warp keeps rows 0, 1 of its group, the upper one rows 2, 3
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) acc[r][s] += __shfl_xor_sync(0xffffffffu, acc[r][s], 16);
+        if (staged) __syncwarp();  // every lane is done reading X: its head becomes the output stage
+        double* oq = X;              // [8][2N]
+        double* od = X + 8 * two_n;  // [8]
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int out = row_out[r0 + 2 * par + rr];
             if (out < 0) continue;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const int slot = 4 * h + s;
-                if (slot < nb) {
-                    const double val = (r == 0 ? acc0[s] : acc1[s]) / Rd;
-                    const long long b = b0 + slot;
-                    if (out == 0) {
-                        dc[b] = val;
-                    } else {
-                        qi[b * static_cast<long long>(2 * N) + (out - 1)] = val;
-                    }
+                const int slot = 4 * hb + s;
+                const double val = (par == 0 ? acc[rr][s] : acc[2 + rr][s]) * inv_r;
+                if (staged) {
+                    if (out == 0) od[slot] = val; else oq[slot * two_n + (out - 1)] = val;
+                } else if (slot < nb) {
+                    if (out == 0) dc[b0 + slot] = val; else qi[(b0 + slot) * static_cast<long long>(two_n) + (out - 1)] = val;
                 }
             }
         }
     }
+    if (staged) {
+        __syncwarp();
+        double2* dst = reinterpret_cast<double2*>(qi + b0 * static_cast<long long>(two_n));  // 16-byte aligned: b0 % 8 == 0
+        const double2* src = reinterpret_cast<const double2*>(X);
+        for (int i = lane; i < nb * N; i += 32) dst[i] = src[i];
+        if (lane < nb) dc[b0 + lane] = X[8 * two_n + lane];
+        __syncwarp();  // the stage is X again for the next group
+    }
 }
 
-__global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const PeriodParams p) {
+template <int WARPS>
+__global__ void __launch_bounds__((WARPS + 1) * 32, 1) demod_period_kernel(const PeriodParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const PeriodSmem L = period_smem_layout(p.P, p.N, p.nstages);
+    const PeriodSmem L = period_smem_layout(p.P, p.N, p.nstages, WARPS);
     double* stage_base = reinterpret_cast<double*>(smem_raw + L.off_stage);
     double* T = reinterpret_cast<double*>(smem_raw + L.off_t);
     int* row_type = reinterpret_cast<int*>(smem_raw + L.off_rows);
@@ -1052,9 +1088,9 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
         *issued = 0ull;
         mbar_fence_init();
     }
-    period_build_tables(P, N, nrows, L.quarter, T, row_type, row_out, tid, kFoldThreads);
+    period_build_tables(P, N, nrows, L.quarter, T, row_type, row_out, tid, (WARPS + 1) * 32);
 
-    if (warp == kFoldConsumerWarps) {
+    if (warp == WARPS) {
         if (lane == 0) {
             const uint64_t pol = l2_evict_first_policy();
             int stage = 0;
@@ -1080,15 +1116,21 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_period_kernel(const Per
     }
 
     double* X = reinterpret_cast<double*>(smem_raw + L.off_x) + warp * L.x_per_warp;
-    for (long long i = warp; i < my_groups; i += kFoldConsumerWarps) {
+    const bool own_stage = (p.nstages % WARPS) == 0;
+    for (long long i = warp; i < my_groups; i += WARPS) {
         const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
         const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
         const int stage = static_cast<int>(i % p.nstages);
         const uint32_t phase = static_cast<uint32_t>((i / p.nstages) & 1);
-        while (*issued <= static_cast<unsigned long long>(i)) __nanosleep(64);
-        __threadfence_block();
+        // A parity wait is only sound once the stage's previous occupant has landed.  When the ring depth is a
+        // multiple of the consumer warps, a stage always belongs to the same warp, which consumed that occupant itself;
+        // otherwise wait until the producer has issued this group (it could not before the occupant was released).
+        if (!own_stage) {
+            while (*issued <= static_cast<unsigned long long>(i)) __nanosleep(64);
+            __threadfence_block();
+        }
         mbar_wait(&full[stage], phase);
-        period_combos(stage_base + static_cast<size_t>(stage) * L.stage_doubles, X, P, L.xrow, nb, lane);
+        period_combos(stage_base + static_cast<size_t>(stage) * L.stage_doubles, X, P, L.xrow, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         period_product(X, T, row_type, row_out, P, N, nrows, L.xrow, nb, b0, p.qi, p.dc, lane);

@@ -27,7 +27,7 @@ struct SweepSmem {
 
 inline __host__ __device__ SweepSmem sweep_smem_layout(int P, int N) {
     SweepSmem S;
-    S.period = period_smem_layout(P, N, 0);
+    S.period = period_smem_layout(P, N, 0, kFoldConsumerWarps);
     size_t o = 0;
     S.period.off_t = o;
     o += static_cast<size_t>(S.period.quarter + 1) * S.period.nrows * 8;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_period_kernel(const Sw
             if (lane == 0) mbar_arrive(&full[pair]);
         } else {
             mbar_wait(&full[pair], phase);
-            period_combos(stage, X, P, L.xrow, nb, lane);
+            period_combos(stage, X, P, L.xrow, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[pair]);
             period_product(X, T, row_type, row_out, P, N, L.nrows, L.xrow, nb, b0, p.qi, p.dc, lane);
