@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_period_kernel(const Sw
     double* stage = reinterpret_cast<double*>(smem_raw + S.off_stage) + static_cast<size_t>(pair) * NBW * P;
     double* X = reinterpret_cast<double*>(smem_raw + S.off_x) + pair * L.x_per_warp;
     const int quads = P >> 2;  // P % 4 == 0
+    // floor(i / quads) = umulhi(i, ceil(2^32 / quads)) for i < 2^16 (here i < 8 * 64)
+    const unsigned quads_magic = static_cast<unsigned>((0x100000000ull + quads - 1) / quads);
     const long long ngroups = (p.nbuf + NBW - 1) / NBW;
     uint32_t phase = 0;
     for (long long g = static_cast<long long>(blockIdx.x) * kFoldConsumerWarps + pair; g < ngroups;
@@ -92,9 +94,9 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_period_kernel(const Sw
         if (generator) {
             mbar_wait(&empty[pair], phase ^ 1u);  // the first wait passes: nothing to free yet
             for (int i = lane; i < nb * quads; i += 32) {
-                const int s = i / quads, q = i - s * quads;
+                const int s = static_cast<int>(__umulhi(static_cast<unsigned>(i), quads_magic)), q = i - s * quads;  // i / quads
                 double y[4];
-                synth_quad_values(p.synth, 1, clean, p.phi, sigma, p.c0 + b0 + s, q, y);
+                synth_quad_values<true>(p.synth, 1, clean, p.phi, sigma, p.c0 + b0 + s, q, y);
                 double2* dst = reinterpret_cast<double2*>(stage + s * P + 4 * q);
                 dst[0] = make_double2(y[0], y[1]);
                 dst[1] = make_double2(y[2], y[3]);

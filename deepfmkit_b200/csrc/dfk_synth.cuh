@@ -55,7 +55,9 @@ DFK_D double synth_clean(const SynthParams& p, double phi, long long t) {
     return p.amp * (1.0 + p.vis * cos(phi + p.m * th));
 }
 
-// The four samples t = 4q .. 4q+3 of channel c.
+// The four samples t = 4q .. 4q+3 of channel c.  FIRST_PERIOD: the caller guarantees 4q + 3 < P (a record of one
+// period), which spares the 64-bit remainder that finds the quad's place in the tabulated period.
+template <bool FIRST_PERIOD = false>
 DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
                              long long q, double y[4]) {
     const unsigned long long key = p.seed + static_cast<unsigned long long>(c);
@@ -68,13 +70,14 @@ DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clea
         box_muller(r[2 * h], r[2 * h + 1], z[2 * h], z[2 * h + 1]);
     }
     const long long t4 = q << 2;
-    int jm = table ? static_cast<int>(t4 % p.P) : 0;
+    int jm = table ? (FIRST_PERIOD ? static_cast<int>(t4) : static_cast<int>(t4 % p.P)) : 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         double clean;
         if (table) {
             clean = clean_tab[jm];
-            if (++jm == p.P) jm = 0;
+            if (!FIRST_PERIOD && ++jm == p.P) jm = 0;
+            if (FIRST_PERIOD) ++jm;
         } else {
             clean = synth_clean(p, phi, t4 + e);
         }
