@@ -31,11 +31,11 @@ size_t dtype_bytes(int dtype) {
 
 // pread of [off, off+n) into dst by a few threads (the page cache copies at memcpy speed per thread)
 int parallel_pread(int fd, void* dst, int64_t off, size_t n) {
-    unsigned hw = std::thread::hardware_concurrency();
-    const int nt = static_cast<int>(std::min<size_t>(hw ? std::min(hw, 8u) : 4u, n / (8u << 20) + 1));
+    CopyPool& pool = CopyPool::instance();
+    const int nt = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::min(pool.size(), 8)), n / (8u << 20) + 1));
     std::vector<int> rc(nt, 0);
-    auto work = [&](int t) {
-        const size_t chunk = ((n / nt) + 4095) & ~static_cast<size_t>(4095);
+    const size_t chunk = ((n / nt) + 4095) & ~static_cast<size_t>(4095);
+    pool.run(nt, [&](int t) {
         size_t lo = std::min(n, chunk * t), hi = std::min(n, chunk * (t + 1));
         while (lo < hi) {
             const ssize_t got = pread(fd, static_cast<char*>(dst) + lo, hi - lo, off + static_cast<int64_t>(lo));
@@ -46,14 +46,7 @@ int parallel_pread(int fd, void* dst, int64_t off, size_t n) {
             }
             lo += static_cast<size_t>(got);
         }
-    };
-    if (nt <= 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nt; ++t) pool.emplace_back(work, t);
-        for (auto& th : pool) th.join();
-    }
+    });
     for (int r : rc)
         if (r) return fail(DFK_ERR_ARG, "short read at offset %lld: %s", (long long)off, std::strerror(errno));
     return DFK_OK;
