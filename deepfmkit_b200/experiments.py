@@ -169,11 +169,13 @@ class Experiment:
         cached = {}
         for point, j, counter, params in self._jobs():
             key = point if not self.stochastic_vars else None
-            cfg = cached.get(key) if key is not None else None
-            if cfg is None:
-                cfg = self.config_factory(params)
-                if key is not None:
-                    cached[key] = cfg
+            hit = cached.get(key) if key is not None else None
+            if hit is not None:  # same physics as the point's first trial: only the noise key differs
+                records[counter] = hit[0]
+                records[counter, 14] = float(counter)
+                df_of[counter] = hit[1]
+                continue
+            cfg = self.config_factory(params)
             if "witness_ifo_config" in cfg:
                 raise NotImplementedError("witness channels belong to the W-DFMI fitters, which are outside this package")
             laser, ifo = cfg["laser_config"], cfg["main_ifo_config"]
@@ -187,6 +189,8 @@ class Experiment:
                 raise NotImplementedError("all trials of an experiment must share the modulation frequency")
             records[counter] = pack_asd_trial(laser, ifo, f_samp, counter, tables, dynamic=True)
             df_of[counter] = laser.df
+            if key is not None:
+                cached[key] = (records[counter].copy(), laser.df)
 
         # ---- 2. simulate and fit in waves ----------------------------------------------------------------------------
         dev = torch.device("cuda", device)
