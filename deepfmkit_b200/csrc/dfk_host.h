@@ -176,8 +176,10 @@ inline bool is_pageable(const void* p) {
 class CopyPool {
 public:
     static CopyPool& instance() {
-        static CopyPool pool;
-        return pool;
+        // never destroyed: its threads end with the process, so nothing is joined during static destruction (or in a
+        // forked child, where the threads do not exist)
+        static CopyPool* pool = new CopyPool();
+        return *pool;
     }
     // run fn(t) for t in [0, n) on the pool's threads (the caller takes a share) and wait
     template <class Fn>
