@@ -595,12 +595,16 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
         double* qs = static_cast<double*>(ctx->qi_seed.ptr);
         double* ds = static_cast<double*>(ctx->dc_seed.ptr);
         cudaStream_t aux = ctx->aux_stream;
+        // The seed demodulation (C buffers: microseconds) goes first on the MAIN stream: it is itself a persistent
+        // shared-memory-filling launch, and queued beside the record's demodulation it would wait for that one to end
+        // whenever the GPU is already busy at enqueue time (back-to-back calls: measured +1.2 ms on the cfg-3 wave).
+        // Only the cold fits -- one-warp blocks that fit beside a demodulation CTA -- run on the side stream.
+        rc = launch_demod(ctx, x, C, 1, ld_c, R, N, w0, qs, ds, st);
+        if (rc) return rc;
         DFK_CUDA(cudaEventRecord(ctx->fork, st));
         DFK_CUDA(cudaStreamWaitEvent(aux, ctx->fork, 0));
         {
             ProfScope ps(ctx, 2, aux);
-            rc = launch_demod(ctx, x, C, 1, ld_c, R, N, w0, qs, ds, aux);
-            if (rc) return rc;
             const dfk::GuessSrc cold_c = init_dev ? guess_rows(init_dev, init_stride, 1, false) : guess_value(init);
             rc = launch_lm(ctx, qs, C, {1, 0, bpc}, N, cold_c, ds, opts, rows, aux);
             if (rc) return rc;
@@ -727,7 +731,13 @@ int dfk_create(int device, dfk_ctx** out) {
     }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // the side stream carries the short cold-seed chain that must start beside a persistent demodulation launch
+        // queued at the same moment: highest priority, so that its few one-warp blocks are placed first
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
