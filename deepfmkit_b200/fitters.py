@@ -182,10 +182,12 @@ class EKFFitter(BaseFitter):
 # additive batch API
 # ------------------------------------------------------------------------------------------------------
 def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_psi=0.0, seeded=True, device=0,
-                  tunables_from=None, return_tensor=False):
+                  tunables_from=None, return_tensor=False, time_major=False):
     """NLS readout of C channel records in one pass.
 
     x: ``[C, T]`` float64 -- a numpy array (copied to the GPU) or a CUDA torch tensor (used in place).
+    time_major: x is ``[T, C]`` (interleaved channels, what acquisition hardware and the DFMSWPM text format produce);
+    it is brought to channel-major on the device by the ingest transpose (one extra read + write pass) first.
     init_m (and init_a, init_psi) may be scalars or length-C arrays (per-channel cold starts, the CRLB
     sweep recipe of workers.py:167-173 with ``seeded=False`` and one buffer per realisation).
     seeded: False -> independent cold starts; True -> every buffer from its channel's buffer 0; an int k ->
@@ -201,6 +203,16 @@ def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_ps
     if xt.dtype != torch.float64:
         raise TypeError("records must be float64")
     xt = xt.to(dev, non_blocking=False).contiguous()
+    if time_major:
+        T_, C_ = xt.shape
+        xc = torch.empty((C_, T_), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            ctx.use_torch_stream()
+            try:
+                ctx.widen_dev(xt.data_ptr(), "float64", T_, C_, True, xc.data_ptr(), max(T_, 1))
+            finally:
+                ctx.use_default_stream()
+        xt = xc
     C, T = xt.shape
     R = int(f_samp / f_mod * n)
     bpc = T // R

@@ -661,3 +661,13 @@ def test_fused_sweep_equals_generate_then_demodulate(torch_mod, ctx, R, nh, nbuf
                         seed=seed)
     ctx.synchronize()
     assert torch_mod.equal(qi0, qi1) and torch_mod.equal(dc0, dc1)
+
+
+def test_time_major_batch_equals_channel_major(torch_mod):
+    """Interleaved [T, C] records (the layout of acquisition hardware) through the device transpose: same rows."""
+    from deepfmkit_b200 import nls_fit_batch
+    xs = np.stack([orc.snr_signal(6.0 + 0.5 * c, 200e3, 1000.0, 0.1, 40.0, seed=c, phi0=0.2 * c) for c in range(5)])
+    a = nls_fit_batch(xs, 200e3, 1000.0, 20)
+    b = nls_fit_batch(np.ascontiguousarray(xs.T), 200e3, 1000.0, 20, time_major=True)
+    c = nls_fit_batch(torch_mod.from_numpy(np.ascontiguousarray(xs.T)).cuda(), 200e3, 1000.0, 20, time_major=True, return_tensor=True)
+    assert np.array_equal(a, b) and np.array_equal(a, c.cpu().numpy())
