@@ -1,6 +1,6 @@
 """Randomised geometry sweep of the TMA-fed demodulation kernels against a plain numpy lock-in.
 
-The ring protocols of the fold / tile / single-period kernels (mbarrier phases, the issued-chunk counter, per-warp
+The ring protocols of the fold / long-fold / tile / single-period kernels (mbarrier phases, the issued-chunk counter, per-warp
 ownership of stages) fail as hangs or as stale data, and which warp meets which stage depends on the number of
 buffers, the ring depth and the group size -- so the sweep draws those at random (fixed seed) and repeats every
 launch, comparing with an independent CPU result.  compute-sanitizer is not available on this pool; this is the
@@ -32,8 +32,8 @@ def test_random_geometries(monkeypatch):
     rng = np.random.RandomState(31337)
     worst = 0.0
     cases = 0
-    for trial in range(70):
-        kind = trial % 5
+    for trial in range(84):
+        kind = trial % 6
         if kind == 0:    # single-period kernel: P % 4 == 0, n = 1
             P, n = 4 * rng.randint(1, 65), 1
         elif kind == 1:  # tile kernel, grouped buffers
@@ -42,8 +42,10 @@ def test_random_geometries(monkeypatch):
             P, n = 2 * rng.randint(20, 129), rng.randint(8, 40)
         elif kind == 3:  # fold kernel
             P, n = 2 * rng.randint(129, 1025), rng.randint(1, 9)
-        else:            # odd period folded over two periods
+        elif kind == 4:  # odd period folded over two periods
             P, n = 2 * rng.randint(3, 300) + 1, 2 * rng.randint(1, 8)
+        else:            # fold lengths beyond 2048: the column-chunked kernel (ragged last chunk included)
+            P, n = 2 * rng.randint(1025, 6000), rng.randint(1, 7)
         nh = int(rng.randint(1, 21))
         nbuf = int(rng.choice([1, 2, 7, 8, 9, 63, 148, 149, 300, 1185, 2371, 5000]))
         if P * n * nbuf > 40_000_000:
@@ -53,6 +55,9 @@ def test_random_geometries(monkeypatch):
         lib.dfk_dev_clear()
         if rng.rand() < 0.3:
             lib.dfk_dev_set(b"DFK_TILE_NSTAGES", int(rng.randint(2, 6)))
+        if kind == 0 and rng.rand() < 0.6:  # consumer warps and ring depth of the single-period kernel
+            lib.dfk_dev_set(b"DFK_PERIOD_WARPS", int(rng.choice([6, 8, 10, 12])))
+            lib.dfk_dev_set(b"DFK_PERIOD_NSTAGES", int(rng.randint(2, 13)))
         t = np.arange(nbuf * R)
         x = 1.0 + np.cos(0.3 + 4.0 * np.cos(2 * np.pi * t / P + 0.1)) + 0.05 * rng.randn(nbuf * R)
         ref_qi, ref_dc = numpy_lockin(x, R, nh, w0)
@@ -70,7 +75,7 @@ def test_random_geometries(monkeypatch):
         cases += 1
     lib.dfk_dev_clear()
     ctx.close()
-    assert cases == 70 and worst <= 1e-12
+    assert cases == 84 and worst <= 1e-12
 
 
 @pytest.mark.parametrize("pinned", [False, True])
