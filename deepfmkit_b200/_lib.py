@@ -81,6 +81,9 @@ SYMBOLS = {
     "dfk_nls_fit_seeded_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _d, c_double_p, _i32, ctypes.POINTER(LmOpts), _vp]),
     "dfk_nls_fit_batch_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
                                              ctypes.POINTER(LmOpts), _vp]),
+    "dfk_demod_tm_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i32, _d, _vp, _vp]),
+    "dfk_nls_fit_batch_tm_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i32, _d, c_double_p, _vp, _i64, _i32,
+                                                ctypes.POINTER(LmOpts), _vp]),
     "dfk_ekf_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _vp]),
     "dfk_ekf_stream_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _d, _d, ctypes.POINTER(EkfOpts), _i64,
                                           _vp, _vp]),
@@ -291,6 +294,17 @@ class Context:
         _check(self.lib, self.lib.dfk_nls_fit_batch_dev(self._h, x_ptr, C, bufs_per_channel, ld_c, R, N, w0, init_arr,
                                                         init_dev_ptr, init_stride, schedule_code(seeded),
                                                         ctypes.byref(opts) if opts is not None else None, rows_ptr))
+
+    def demod_tm(self, x_ptr, bufs_per_channel, C, R, N, w0, qi_ptr, dc_ptr):
+        _check(self.lib, self.lib.dfk_demod_tm_dev(self._h, x_ptr, int(bufs_per_channel), int(C), int(R), int(N), float(w0),
+                                                   qi_ptr, dc_ptr))
+
+    def nls_fit_batch_tm_dev(self, x_ptr, C, bufs_per_channel, R, N, w0, init, init_dev_ptr, init_stride, seeded, opts, rows_ptr):
+        init_arr = (ctypes.c_double * 4)(*[float(v) for v in init]) if init is not None else None
+        _check(self.lib, self.lib.dfk_nls_fit_batch_tm_dev(self._h, x_ptr, int(C), int(bufs_per_channel), int(R), int(N),
+                                                           float(w0), init_arr, init_dev_ptr, int(init_stride),
+                                                           schedule_code(seeded),
+                                                           ctypes.byref(opts) if opts is not None else None, rows_ptr))
 
     def ekf_dev(self, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod, opts, rows_ptr):
         _check(self.lib, self.lib.dfk_ekf_dev(self._h, z_ptr, T, C, ld_t, ld_c, R, f_samp, f_mod,

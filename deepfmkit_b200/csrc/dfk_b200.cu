@@ -351,6 +351,69 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
 }
 
 // ---- LM -------------------------------------------------------------------------------------------
+// Lock-in of a time-major record x[t * C + c]: nbuf_t buffers of R time steps, all C channels; harmonic vectors and
+// means of unit u = c * nbuf_t + b.  The interleaved buffer folds like one channel of period P C (column-chunked fold
+// kernel in STORE mode: every sample read once), then the per-channel harmonics are taken from the folded arrays.
+// Returns DFK_ERR_ARG for geometries that cannot fold (the caller then transposes and takes the channel-major path).
+int launch_demod_tm(dfk_ctx* ctx, const double* x, int64_t nbuf_t, int64_t C, int64_t R, int32_t N, double w0, double* qi,
+                    double* dc, cudaStream_t st) {
+    if (nbuf_t == 0 || C == 0) return DFK_OK;
+    const dfk::DemodPlan pl = dfk::make_demod_plan(R, w0, N);
+    const int64_t Pc = pl.P * C, Rc = R * C;
+    if (!pl.folded || (Pc & 1) || Pc > dfk::kMaxFoldPeriod || Rc > std::numeric_limits<int>::max() ||
+        (reinterpret_cast<uintptr_t>(x) & 15u) != 0)
+        return fail(DFK_ERR_ARG, "time-major record does not fold (period %lld x %lld channels)", (long long)pl.P, (long long)C);
+    const size_t fold_doubles = static_cast<size_t>(nbuf_t) * static_cast<size_t>(Pc);
+    int rc = ensure(ctx, ctx->post[6], fold_doubles * sizeof(double) * (pl.drift ? 2 : 1));
+    if (!rc) rc = ensure(ctx, ctx->post[7], sizeof(double) * dfk::kMaxHarmonics);
+    if (rc) return rc;
+    double* fs = static_cast<double*>(ctx->post[6].ptr);
+    double* ft = pl.drift ? fs + fold_doubles : fs;
+    double* delta_dev = static_cast<double*>(ctx->post[7].ptr);
+    DFK_CUDA(cudaMemcpyAsync(delta_dev, pl.delta, sizeof(double) * dfk::kMaxHarmonics, cudaMemcpyHostToDevice, st));
+    dfk::FoldParams p;
+    p.x = x;
+    p.qi = fs;
+    p.dc = ft;
+    p.nbuf = nbuf_t;
+    p.bpc = nbuf_t;
+    p.ld_c = 0;
+    p.R = static_cast<int>(Rc);
+    p.P = static_cast<int>(Pc);
+    p.periods = static_cast<int>(pl.periods);
+    p.N = N;
+    p.kmul = pl.kmul;
+    p.pps = static_cast<int>(std::min<int64_t>(2, pl.periods));
+    for (int k = 0; k < dfk::kMaxHarmonics; ++k) p.delta[k] = pl.delta[k];
+    int nst = 6;
+    size_t smem = 0;
+    for (; nst >= 2; --nst) {
+        smem = dfk::fold_long_smem_layout(p.pps, nst, N, pl.drift).total;
+        if (smem <= static_cast<size_t>(ctx->max_smem_optin)) break;
+    }
+    if (nst < 2) return fail(DFK_ERR_ARG, "no shared memory for the time-major fold");
+    p.nstages = nst;
+    const int grid = static_cast<int>(std::min<int64_t>(nbuf_t, ctx->sm_count));
+    const int64_t units = nbuf_t * C;
+    const unsigned pgrid = static_cast<unsigned>((units + 127) / 128);
+    if (pl.drift) {
+        DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_long_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        dfk::demod_fold_long_kernel<true, true><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+        dfk::project_interleaved_kernel<true><<<pgrid, 128, 0, st>>>(fs, ft, nbuf_t, static_cast<int>(C), static_cast<int>(pl.P),
+                                                                      static_cast<int>(R), N, pl.kmul, delta_dev, qi, dc);
+    } else {
+        DFK_CUDA(cudaFuncSetAttribute(dfk::demod_fold_long_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        dfk::demod_fold_long_kernel<false, true><<<grid, dfk::kFoldThreads, smem, st>>>(p);
+        dfk::project_interleaved_kernel<false><<<pgrid, 128, 0, st>>>(fs, ft, nbuf_t, static_cast<int>(C), static_cast<int>(pl.P),
+                                                                       static_cast<int>(R), N, pl.kmul, delta_dev, qi, dc);
+    }
+    ctx->launches += 2;
+    DFK_CUDA(cudaGetLastError());
+    return DFK_OK;
+}
+
 int pick_lanes(const dfk_ctx* ctx, int64_t nfit, int N, int requested) {
     if (requested == 1 || requested == 2 || requested == 4 || requested == 8 || requested == 16 || requested == 32)
         return requested;
@@ -566,7 +629,7 @@ dfk::ChainPlan chain_plan(const Schedule& sc, int64_t bpc) {
 //   seed_row (single-channel continuation slabs only): the row that already holds buffer 0's result.
 int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
                   const double init[4], const double* init_dev, int64_t init_stride, const Schedule& sc,
-                  const double* seed_row, const dfk_lm_opts* opts, double* rows, cudaStream_t st) {
+                  const double* seed_row, const dfk_lm_opts* opts, double* rows, cudaStream_t st, bool time_major = false) {
     const int64_t nbuf = C * bpc;
     if (nbuf == 0) return DFK_OK;
     int rc = ensure(ctx, ctx->qi, static_cast<size_t>(nbuf) * 2 * N * sizeof(double));
@@ -599,7 +662,7 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
         // shared-memory-filling launch, and queued beside the record's demodulation it would wait for that one to end
         // whenever the GPU is already busy at enqueue time (back-to-back calls: measured +1.2 ms on the cfg-3 wave).
         // Only the cold fits -- one-warp blocks that fit beside a demodulation CTA -- run on the side stream.
-        rc = launch_demod(ctx, x, C, 1, ld_c, R, N, w0, qs, ds, st);
+        rc = time_major ? launch_demod_tm(ctx, x, 1, C, R, N, w0, qs, ds, st) : launch_demod(ctx, x, C, 1, ld_c, R, N, w0, qs, ds, st);
         if (rc) return rc;
         DFK_CUDA(cudaEventRecord(ctx->fork, st));
         DFK_CUDA(cudaStreamWaitEvent(aux, ctx->fork, 0));
@@ -613,7 +676,8 @@ int nls_on_device(dfk_ctx* ctx, const double* x, int64_t C, int64_t bpc, int64_t
     }
     {
         ProfScope ps(ctx, 0, st);
-        rc = launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st, two_stage);
+        rc = time_major ? launch_demod_tm(ctx, x, bpc, C, R, N, w0, qi, dc, st)
+                        : launch_demod(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st, two_stage);
     }
     if (rc) return rc;
     if (two_stage) DFK_CUDA(cudaStreamWaitEvent(st, ctx->join, 0));  // before the LM timing scope opens
@@ -866,6 +930,33 @@ int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t 
     return nls_on_device(ctx, x_dev, C, bufs_per_channel, ld_c, R, N, w0, init ? init : zero, init_dev, init_stride,
                          schedule_of(seeded), nullptr, opts, rows_dev, ctx->stream());
 }
+
+int dfk_demod_tm_dev(dfk_ctx* ctx, const double* x_dev, int64_t bufs_per_channel, int64_t C, int64_t R, int32_t N, double w0,
+                     double* qi_dev, double* dc_dev) {
+    DFK_ENTER(ctx);
+    if (C < 0 || bufs_per_channel < 0) return fail(DFK_ERR_ARG, "negative channel or buffer count");
+    const int rc = check_nls_args(C * bufs_per_channel, R, N, w0);
+    if (rc) return rc;
+    if (C * bufs_per_channel > 0 && (!x_dev || !qi_dev || !dc_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    ProfScope ps(ctx, 0, ctx->stream());
+    return launch_demod_tm(ctx, x_dev, bufs_per_channel, C, R, N, w0, qi_dev, dc_dev, ctx->stream());
+}
+
+int dfk_nls_fit_batch_tm_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t R, int32_t N,
+                             double w0, const double init[4], const double* init_dev, int64_t init_stride, int32_t seeded,
+                             const dfk_lm_opts* opts, double* rows_dev) {
+    DFK_ENTER(ctx);
+    if (C < 0 || bufs_per_channel < 0) return fail(DFK_ERR_ARG, "negative channel or buffer count");
+    const int rc = check_nls_args(C * bufs_per_channel, R, N, w0);
+    if (rc) return rc;
+    if (!init && !init_dev) return fail(DFK_ERR_ARG, "no initial guess");
+    if (init_dev && init_stride < 4) return fail(DFK_ERR_ARG, "init_stride must be >= 4");
+    if (C * bufs_per_channel > 0 && (!x_dev || !rows_dev)) return fail(DFK_ERR_ARG, "null device pointer");
+    const double zero[4] = {0, 0, 0, 0};
+    return nls_on_device(ctx, x_dev, C, bufs_per_channel, 0, R, N, w0, init ? init : zero, init_dev, init_stride,
+                         schedule_of(seeded), nullptr, opts, rows_dev, ctx->stream(), true);
+}
+
 
 static int nls_host_impl(dfk_ctx* ctx, const double* x_host, int64_t nsamp, int64_t R, int32_t N, double w0,
                          const double init[4], Schedule sc, const dfk_lm_opts* opts, double* rows_host);

@@ -318,7 +318,11 @@ inline __host__ __device__ FoldLongSmem fold_long_smem_layout(int pps, int nstag
     return L;
 }
 
-template <bool DRIFT>
+// STORE: instead of projecting, the folded sums S (and, with DRIFT, T_g = sum_k k x[g + k P]) of every buffer are
+// written out -- p.qi and p.dc then point at [nbuf][P] scratch arrays.  That is the first half of the lock-in of
+// time-major records (fold_interleaved below): an interleaved [T][C] buffer folds like a single channel whose period is
+// P C samples, and the per-channel harmonics are taken from the folded super-period by project_interleaved_kernel.
+template <bool DRIFT, bool STORE = false>
 __global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const FoldParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FoldLongSmem L = fold_long_smem_layout(p.pps, p.nstages, p.N, DRIFT);
@@ -429,6 +433,19 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const 
                     phase ^= 1u;
                 }
             }
+            if (STORE) {
+                double2* fs = reinterpret_cast<double2*>(p.qi + b * static_cast<long long>(P) + static_cast<long long>(w) * kLongChunk);
+                double2* ft = reinterpret_cast<double2*>(p.dc + b * static_cast<long long>(P) + static_cast<long long>(w) * kLongChunk);
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int pair = tid + s * kFoldConsumers;
+                    if (pair < whalf) {
+                        fs[pair] = accS[s];
+                        if (DRIFT) ft[pair] = accT[s];
+                    }
+                }
+                continue;
+            }
             consumer_bar();  // the previous chunk's projection is over
 #pragma unroll
             for (int s = 0; s < SLOTS; ++s) {
@@ -488,6 +505,7 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const 
                 }
             }
         }
+        if (STORE) continue;
         int pass = 0;
         for (int k0 = warp; k0 <= N; k0 += 2 * kFoldConsumerWarps, ++pass) {
             const int k1 = k0 + kFoldConsumerWarps;
@@ -529,6 +547,83 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const 
                         out[N + k - 1] = iv / Rd;
                     }
                 }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// project_interleaved_kernel -- second half of the time-major lock-in.  fs[b][j][c] (and ft) hold the folded sums of
+// time buffer b, time column j of the period, channel c; a thread takes one (buffer, channel), walks the P columns
+// (adjacent threads read adjacent channels: coalesced) and accumulates kProjBlock harmonics at a time with a rotation
+// recurrence restarted from an exact sincospi every kProjResync columns.  Output rows are channel-major:
+// unit u = c * bpc + b.  The folded arrays are 1/n of the record (n periods per buffer), so this pass reads little.
+constexpr int kProjBlock = 6;
+constexpr int kProjResync = 32;
+
+template <bool DRIFT>
+__global__ void __launch_bounds__(128) project_interleaved_kernel(const double* __restrict__ fs, const double* __restrict__ ft,
+                                                                   long long nbuf_t, int C, int P, int R, int N, int kmul,
+                                                                   const double* __restrict__ delta, double* __restrict__ qi,
+                                                                   double* __restrict__ dc) {
+    const long long idx = blockIdx.x * 128ll + threadIdx.x;
+    if (idx >= nbuf_t * C) return;
+    const long long b = idx / C;
+    const int c = static_cast<int>(idx - b * C);
+    const double* s = fs + (b * P) * static_cast<long long>(C) + c;
+    const double* t = DRIFT ? ft + (b * P) * static_cast<long long>(C) + c : nullptr;
+    const double Rd = static_cast<double>(R);
+    const long long u = static_cast<long long>(c) * nbuf_t + b;
+    double* out = qi + u * static_cast<long long>(2 * N);
+    const double Pd = static_cast<double>(P);
+    for (int k0 = 0; k0 <= N; k0 += kProjBlock) {
+        double aq[kProjBlock], ai[kProjBlock], uq[kProjBlock], ui[kProjBlock], cs[kProjBlock], sn[kProjBlock], cst[kProjBlock],
+            snt[kProjBlock];
+#pragma unroll
+        for (int h = 0; h < kProjBlock; ++h) {
+            aq[h] = ai[h] = uq[h] = ui[h] = 0.0;
+            const long long r1 = (static_cast<long long>(k0 + h) * kmul) % P;
+            sincospi(2.0 * static_cast<double>(r1) / Pd, &snt[h], &cst[h]);  // one-column step of harmonic k0 + h
+        }
+        for (int j0 = 0; j0 < P; j0 += kProjResync) {
+#pragma unroll
+            for (int h = 0; h < kProjBlock; ++h) {
+                const long long r0 = (static_cast<long long>(k0 + h) * kmul * j0) % P;
+                sincospi(2.0 * static_cast<double>(r0) / Pd, &sn[h], &cs[h]);
+            }
+            const int j1 = min(P, j0 + kProjResync);
+            for (int j = j0; j < j1; ++j) {
+                const double v = s[static_cast<long long>(j) * C];
+                double w = 0.0;
+                if (DRIFT) w = fma(Pd, t[static_cast<long long>(j) * C], static_cast<double>(j) * v);  // U_j = j S_j + P T_j
+#pragma unroll
+                for (int h = 0; h < kProjBlock; ++h) {
+                    aq[h] = fma(v, cs[h], aq[h]);
+                    ai[h] = fma(v, sn[h], ai[h]);
+                    if (DRIFT) {
+                        uq[h] = fma(w, sn[h], uq[h]);
+                        ui[h] = fma(w, cs[h], ui[h]);
+                    }
+                    const double cn = cs[h] * cst[h] - sn[h] * snt[h];
+                    sn[h] = fma(sn[h], cst[h], cs[h] * snt[h]);
+                    cs[h] = cn;
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < kProjBlock; ++h) {
+            const int k = k0 + h;
+            if (k > N) break;
+            if (k == 0) {
+                dc[u] = aq[h] / Rd;
+            } else {
+                double qv = aq[h], iv = ai[h];
+                if (DRIFT) {
+                    qv = fma(-delta[k - 1], uq[h], qv);
+                    iv = fma(delta[k - 1], ui[h], iv);
+                }
+                out[k - 1] = qv / Rd;
+                out[N + k - 1] = iv / Rd;
             }
         }
     }

@@ -54,7 +54,7 @@ struct dfk_ctx {
     void* stager[kStagers] = {nullptr, nullptr, nullptr};
     cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
     DevBuf qi, dc, retry, counters, slab[2], rows, stats, stats_part, misc, qi_seed, dc_seed;
-    static constexpr int kPostBufs = 6;
+    static constexpr int kPostBufs = 8;
     DevBuf post[kPostBufs];  // scratch of the ingest / spectra / generator entries (dfk_post.cu, dfk_ingest.cu)
     int64_t launches = 0;
     // text record resident in post[3] between dfk_text_load* and dfk_text_parse_dev (dfk_ingest.cu)

@@ -203,17 +203,24 @@ def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_ps
     if xt.dtype != torch.float64:
         raise TypeError("records must be float64")
     xt = xt.to(dev, non_blocking=False).contiguous()
+    native_tm = False
     if time_major:
         T_, C_ = xt.shape
-        xc = torch.empty((C_, T_), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
-            ctx.use_torch_stream()
-            try:
-                ctx.widen_dev(xt.data_ptr(), "float64", T_, C_, True, xc.data_ptr(), max(T_, 1))
-            finally:
-                ctx.use_default_stream()
-        xt = xc
-    C, T = xt.shape
+        R_ = int(f_samp / f_mod * n)
+        # the interleaved record folds in place when its geometry allows (whole even period x channels, whole periods
+        # per buffer); otherwise it is transposed once on the device and takes the channel-major path
+        native_tm = C_ > 0 and T_ >= R_ > 0 and _lib.demod_path(R_, 2.0 * np.pi * f_mod / f_samp) == 1 and \
+            R_ * C_ < 2 ** 31 and not (xt.data_ptr() & 15)
+        if not native_tm:
+            xc = torch.empty((C_, T_), dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                ctx.use_torch_stream()
+                try:
+                    ctx.widen_dev(xt.data_ptr(), "float64", T_, C_, True, xc.data_ptr(), max(T_, 1))
+                finally:
+                    ctx.use_default_stream()
+            xt = xc
+    C, T = (xt.shape[1], xt.shape[0]) if native_tm else xt.shape
     R = int(f_samp / f_mod * n)
     bpc = T // R
     w0 = 2.0 * np.pi * f_mod / f_samp
@@ -234,8 +241,17 @@ def nls_fit_batch(x, f_samp, f_mod, n, ndata=10, init_a=1.6, init_m=6.0, init_ps
     with torch.cuda.device(dev):
         ctx.use_torch_stream()
         try:
-            ctx.nls_fit_batch_dev(xt.data_ptr(), C, bpc, T, R, int(ndata), w0, init, init_dev_ptr, init_stride, seeded,
-                                  fit_tunables.current_lm_opts(tunables_from), rows.data_ptr())
+            if native_tm:
+                try:
+                    ctx.nls_fit_batch_tm_dev(xt.data_ptr(), C, bpc, R, int(ndata), w0, init, init_dev_ptr, init_stride,
+                                             seeded, fit_tunables.current_lm_opts(tunables_from), rows.data_ptr())
+                except RuntimeError:  # a geometry the fold cannot take after all: transpose and go channel-major
+                    xc = torch.empty((C, T), dtype=torch.float64, device=dev)
+                    ctx.widen_dev(xt.data_ptr(), "float64", T, C, True, xc.data_ptr(), max(T, 1))
+                    xt, native_tm = xc, False
+            if not native_tm:
+                ctx.nls_fit_batch_dev(xt.data_ptr(), C, bpc, T, R, int(ndata), w0, init, init_dev_ptr, init_stride, seeded,
+                                      fit_tunables.current_lm_opts(tunables_from), rows.data_ptr())
         finally:
             ctx.use_default_stream()
         torch.cuda.current_stream(dev).synchronize()

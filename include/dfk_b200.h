@@ -172,6 +172,18 @@ int dfk_nls_fit_batch_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t 
                           int64_t R, int32_t N, double w0, const double init[4], const double* init_dev,
                           int64_t init_stride, int32_t seeded, const dfk_lm_opts* opts, double* rows_dev);
 
+/* The same for a TIME-MAJOR record, sample (t, c) at x_dev[t * C + c] (interleaved channels: the layout acquisition
+ * hardware and the DFMSWPM text format produce), without a transposition pass: an interleaved buffer folds like one
+ * channel whose period is C times as long, and the per-channel harmonics are taken from the folded sums.  Needs a
+ * foldable geometry (whole even number of samples per modulation period x C, whole periods per buffer) and fails with
+ * DFK_ERR_ARG otherwise -- transpose with dfk_widen_dev then.  Units are channel-major as above:
+ * rows_dev / qi_dev row c * bufs_per_channel + b. */
+int dfk_demod_tm_dev(dfk_ctx* ctx, const double* x_dev, int64_t bufs_per_channel, int64_t C, int64_t R, int32_t N, double w0,
+                     double* qi_dev, double* dc_dev);
+int dfk_nls_fit_batch_tm_dev(dfk_ctx* ctx, const double* x_dev, int64_t C, int64_t bufs_per_channel, int64_t R, int32_t N,
+                             double w0, const double init[4], const double* init_dev, int64_t init_stride, int32_t seeded,
+                             const dfk_lm_opts* opts, double* rows_dev);
+
 /* 5-state EKF over C independent channels, one thread per channel.
  * Replaces EKFFitter.fit (fitters.py:214-320).  Sample (t, c) is z_dev[t*ld_t + c*ld_c]
  * (time-major: ld_t = C, ld_c = 1; channel-major: ld_t = 1, ld_c = T).

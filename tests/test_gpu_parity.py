@@ -664,10 +664,44 @@ def test_fused_sweep_equals_generate_then_demodulate(torch_mod, ctx, R, nh, nbuf
 
 
 def test_time_major_batch_equals_channel_major(torch_mod):
-    """Interleaved [T, C] records (the layout of acquisition hardware) through the device transpose: same rows."""
+    """Interleaved [T, C] records (the layout of acquisition hardware) folded in place == the channel-major readout."""
     from deepfmkit_b200 import nls_fit_batch
     xs = np.stack([orc.snr_signal(6.0 + 0.5 * c, 200e3, 1000.0, 0.1, 40.0, seed=c, phi0=0.2 * c) for c in range(5)])
     a = nls_fit_batch(xs, 200e3, 1000.0, 20)
     b = nls_fit_batch(np.ascontiguousarray(xs.T), 200e3, 1000.0, 20, time_major=True)
     c = nls_fit_batch(torch_mod.from_numpy(np.ascontiguousarray(xs.T)).cuda(), 200e3, 1000.0, 20, time_major=True, return_tensor=True)
-    assert np.array_equal(a, b) and np.array_equal(a, c.cpu().numpy())
+    assert np.array_equal(b, c.cpu().numpy())
+    assert np.array_equal(a[:, :, 6], b[:, :, 6]) and np.max(np.abs(a[:, :, :4] - b[:, :, :4])) < 1e-9
+    assert np.max(np.abs(a[:, :, 4] - b[:, :, 4])) < 1e-14
+    # a geometry that cannot fold (75 samples per period, one period per buffer): the transposing fallback, same rows
+    ys = np.stack([orc.snr_signal(6.0, 30e3, 400.0, 0.05, 40.0, seed=c) for c in range(3)])
+    a = nls_fit_batch(ys, 30e3, 400.0, 1)
+    b = nls_fit_batch(np.ascontiguousarray(ys.T), 30e3, 400.0, 1, time_major=True)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("P,n,nh,C,nbuf", [(200, 20, 10, 256, 7), (200, 20, 10, 1, 9), (1000, 20, 10, 2, 5), (200, 3, 62, 5, 11),
+                                           (128, 1, 15, 33, 4), (2000, 40, 40, 3, 3), (76, 2, 7, 27, 6)])
+def test_time_major_demod_matches_reference_lockin(torch_mod, ctx, P, n, nh, C, nbuf):
+    """dfk_demod_tm_dev on x[t, c] against the oracle's lock-in of every channel: the drift term on long / many-harmonic
+    buffers, one channel, odd channel counts, super-periods that are no multiple of the 2048-column chunk."""
+    f_mod = 1000.0
+    f_samp = f_mod * P
+    R = P * n
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    rng = np.random.RandomState(P + C)
+    t = np.arange(nbuf * R)
+    x = np.stack([1.0 + np.cos(0.3 * c + (3.0 + 0.01 * c) * np.cos(2 * np.pi * t / P + 0.2)) + 0.01 * rng.randn(nbuf * R)
+                  for c in range(C)], axis=1)  # [T, C]
+    xd = torch_mod.from_numpy(np.ascontiguousarray(x)).cuda()
+    qi = torch_mod.full((C * nbuf, 2 * nh), float("nan"), dtype=torch_mod.float64, device="cuda")
+    dc = torch_mod.full((C * nbuf,), float("nan"), dtype=torch_mod.float64, device="cuda")
+    ctx.demod_tm(xd.data_ptr(), nbuf, C, R, nh, w0, qi.data_ptr(), dc.data_ptr())
+    ctx.synchronize()
+    qi, dc = qi.cpu().numpy().reshape(C, nbuf, 2 * nh), dc.cpu().numpy().reshape(C, nbuf)
+    for c in sorted({0, C // 2, C - 1}):
+        for b in sorted({0, nbuf - 1}):
+            buf = x[b * R:(b + 1) * R, c]
+            ref = orc.lockin_means(buf, w0, nh)
+            assert np.max(np.abs(qi[c, b] - ref)) <= IQ_TOL * max(np.abs(ref).max(), 1e-3), (c, b)
+            assert abs(dc[c, b] - buf.mean()) <= 1e-14 * abs(buf.mean())
