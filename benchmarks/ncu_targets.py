@@ -19,7 +19,7 @@ from deepfmkit_b200 import fit as tun  # noqa: E402
 
 
 def main():
-    what = sys.argv[1:] or ["fold", "ekf", "sweep", "period", "long", "post", "text", "asd", "widen"]
+    what = sys.argv[1:] or ["fold", "ekf", "sweep", "period", "long", "post", "text", "asd", "widen", "tm"]
     ctx = _lib.get_context(0)
     opts = tun.current_lm_opts()
     dev = "cuda"
@@ -68,6 +68,17 @@ def main():
         ctx.demod(x.data_ptr(), C, R, N, 2 * np.pi / 200, qi.data_ptr(), dc.data_ptr())
         torch.cuda.synchronize()
         del x
+    if "tm" in what:  # time-major: 256 channels x 20 s interleaved (8.2 GB)
+        C, T, R, N = 256, 4_000_000, 4000, 10
+        xc = torch.empty((C, T), dtype=torch.float64, device=dev)
+        ctx.synth_snr_dev(xc.data_ptr(), T, C, 200e3, 1000.0, 6.0, dphi=2 * np.pi / C, seed=5)
+        xt = xc.t().contiguous()
+        del xc
+        qi = torch.empty((C * (T // R), 2 * N), dtype=torch.float64, device=dev)
+        dc = torch.empty(C * (T // R), dtype=torch.float64, device=dev)
+        ctx.demod_tm(xt.data_ptr(), T // R, C, R, N, 2 * np.pi / 200, qi.data_ptr(), dc.data_ptr())
+        torch.cuda.synchronize()
+        del xt
     if "text" in what:
         vals = 1.0 + np.random.RandomState(0).randn(1_000_000, 2)
         text = "".join(f"{a!r} {b!r} \n" for a, b in vals.tolist()).encode() * 8

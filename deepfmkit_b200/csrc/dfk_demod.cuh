@@ -554,9 +554,10 @@ __global__ void __launch_bounds__(kFoldThreads, 1) demod_fold_long_kernel(const 
 
 // ---------------------------------------------------------------------------------------------------
 // project_interleaved_kernel -- second half of the time-major lock-in.  fs[b][j][c] (and ft) hold the folded sums of
-// time buffer b, time column j of the period, channel c; a thread takes one (buffer, channel), walks the P columns
-// (adjacent threads read adjacent channels: coalesced) and accumulates kProjBlock harmonics at a time with a rotation
-// recurrence restarted from an exact sincospi every kProjResync columns.  Output rows are channel-major:
+// time buffer b, time column j of the period, channel c; a thread takes one (buffer, channel) and walks the columns
+// (adjacent threads read adjacent channels: coalesced) in j <-> P - j pairs -- the cosine sums need S_j + S_{P-j}, the
+// sine sums S_j - S_{P-j}, which halves the work -- accumulating kProjBlock harmonics at a time with a rotation
+// recurrence restarted from an exact sincospi every kProjResync pairs.  Output rows are channel-major:
 // unit u = c * bpc + b.  The folded arrays are 1/n of the record (n periods per buffer), so this pass reads little.
 constexpr int kProjBlock = 6;
 constexpr int kProjResync = 32;
@@ -576,6 +577,7 @@ __global__ void __launch_bounds__(128) project_interleaved_kernel(const double* 
     const long long u = static_cast<long long>(c) * nbuf_t + b;
     double* out = qi + u * static_cast<long long>(2 * N);
     const double Pd = static_cast<double>(P);
+    const int half = P >> 1;  // P is even
     for (int k0 = 0; k0 <= N; k0 += kProjBlock) {
         double aq[kProjBlock], ai[kProjBlock], uq[kProjBlock], ui[kProjBlock], cs[kProjBlock], sn[kProjBlock], cst[kProjBlock],
             snt[kProjBlock];
@@ -585,28 +587,52 @@ __global__ void __launch_bounds__(128) project_interleaved_kernel(const double* 
             const long long r1 = (static_cast<long long>(k0 + h) * kmul) % P;
             sincospi(2.0 * static_cast<double>(r1) / Pd, &snt[h], &cst[h]);  // one-column step of harmonic k0 + h
         }
-        for (int j0 = 0; j0 < P; j0 += kProjResync) {
+        for (int j0 = 0; j0 <= half; j0 += kProjResync) {
 #pragma unroll
             for (int h = 0; h < kProjBlock; ++h) {
                 const long long r0 = (static_cast<long long>(k0 + h) * kmul * j0) % P;
                 sincospi(2.0 * static_cast<double>(r0) / Pd, &sn[h], &cs[h]);
             }
-            const int j1 = min(P, j0 + kProjResync);
-            for (int j = j0; j < j1; ++j) {
-                const double v = s[static_cast<long long>(j) * C];
-                double w = 0.0;
-                if (DRIFT) w = fma(Pd, t[static_cast<long long>(j) * C], static_cast<double>(j) * v);  // U_j = j S_j + P T_j
+            const int j1 = min(half + 1, j0 + kProjResync);
+            // four column pairs per trip, their (independent, L2 / HBM latency) loads issued before any arithmetic
+            for (int jb = j0; jb < j1; jb += 4) {
+                double v1[4], v2[4], t1[4], t2[4];
 #pragma unroll
-                for (int h = 0; h < kProjBlock; ++h) {
-                    aq[h] = fma(v, cs[h], aq[h]);
-                    ai[h] = fma(v, sn[h], ai[h]);
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb + e;
+                    const bool live = j < j1, self = j == 0 || j == half;
+                    v1[e] = live ? s[static_cast<long long>(j) * C] : 0.0;
+                    v2[e] = (live && !self) ? s[static_cast<long long>(P - j) * C] : 0.0;
                     if (DRIFT) {
-                        uq[h] = fma(w, sn[h], uq[h]);
-                        ui[h] = fma(w, cs[h], ui[h]);
+                        t1[e] = live ? t[static_cast<long long>(j) * C] : 0.0;
+                        t2[e] = (live && !self) ? t[static_cast<long long>(P - j) * C] : 0.0;
                     }
-                    const double cn = cs[h] * cst[h] - sn[h] * snt[h];
-                    sn[h] = fma(sn[h], cst[h], cs[h] * snt[h]);
-                    cs[h] = cn;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = jb + e;
+                    if (j >= j1) break;
+                    const bool self = j == 0 || j == half;  // columns that pair with themselves
+                    const double va = v1[e] + v2[e], vd = self ? 0.0 : v1[e] - v2[e];
+                    double wa = 0.0, wd = 0.0;
+                    if (DRIFT) {  // U_j = j S_j + P T_j
+                        const double w1 = fma(Pd, t1[e], static_cast<double>(j) * v1[e]);
+                        const double w2 = self ? 0.0 : fma(Pd, t2[e], static_cast<double>(P - j) * v2[e]);
+                        wa = w1 + w2;
+                        wd = self ? 0.0 : w1 - w2;
+                    }
+#pragma unroll
+                    for (int h = 0; h < kProjBlock; ++h) {
+                        aq[h] = fma(va, cs[h], aq[h]);
+                        ai[h] = fma(vd, sn[h], ai[h]);
+                        if (DRIFT) {
+                            uq[h] = fma(wd, sn[h], uq[h]);
+                            ui[h] = fma(wa, cs[h], ui[h]);
+                        }
+                        const double cn = cs[h] * cst[h] - sn[h] * snt[h];
+                        sn[h] = fma(sn[h], cst[h], cs[h] * snt[h]);
+                        cs[h] = cn;
+                    }
                 }
             }
         }
