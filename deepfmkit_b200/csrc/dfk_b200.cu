@@ -1282,37 +1282,49 @@ int dfk_sweep_demod_dev(dfk_ctx* ctx, int64_t nbuf, int64_t c0, int64_t R, int32
     // fused path: one whole period per record, the geometry of the quarter-wave kernel, tables that fit the SM
     if (whole && R == P && P <= dfk::kTileMaxPeriod && (P % 4) == 0 && (reinterpret_cast<uintptr_t>(qi_dev) & 15u) == 0 &&
         !dev_int("DFK_NO_SWEEP_FUSE", 0)) {
-        const dfk::SweepSmem S = dfk::sweep_smem_layout(static_cast<int>(P), N);
-        if (S.total <= static_cast<size_t>(ctx->max_smem_optin)) {
-            dfk::SweepParams sp = {};
-            sp.synth.T = P;
-            sp.synth.C = nbuf;
-            sp.synth.P = P;
-            sp.synth.f_ratio = f_mod / f_samp;
-            sp.synth.m = m;
-            sp.synth.amp = amp;
-            sp.synth.vis = visibility;
-            sp.synth.phi0 = phi0;
-            sp.synth.psi0 = psi0;
-            sp.synth.sigma_scale = std::pow(10.0, -snr_db / 20.0);
-            sp.synth.seed = seed;
-            sp.phi = phi0;
-            sp.qi = qi_dev;
-            sp.dc = dc_dev;
-            sp.nbuf = nbuf;
-            sp.c0 = c0;
-            sp.N = N;
-            const int64_t ngroups = (nbuf + dfk::kPeriodNbw - 1) / dfk::kPeriodNbw;
-            const int grid = static_cast<int>(std::min<int64_t>((ngroups + dfk::kFoldConsumerWarps - 1) / dfk::kFoldConsumerWarps,
-                                                               ctx->sm_count));
-            DFK_CUDA(cudaFuncSetAttribute(dfk::sweep_period_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(S.total)));
+        dfk::SweepParams sp = {};
+        sp.synth.T = P;
+        sp.synth.C = nbuf;
+        sp.synth.P = P;
+        sp.synth.f_ratio = f_mod / f_samp;
+        sp.synth.m = m;
+        sp.synth.amp = amp;
+        sp.synth.vis = visibility;
+        sp.synth.phi0 = phi0;
+        sp.synth.psi0 = psi0;
+        sp.synth.sigma_scale = std::pow(10.0, -snr_db / 20.0);
+        sp.synth.seed = seed;
+        sp.phi = phi0;
+        sp.qi = qi_dev;
+        sp.dc = dc_dev;
+        sp.nbuf = nbuf;
+        sp.c0 = c0;
+        sp.N = N;
+        const int64_t ngroups = (nbuf + dfk::kPeriodNbw - 1) / dfk::kPeriodNbw;
+        const int grid = static_cast<int>(std::min<int64_t>(ngroups, ctx->sm_count));
+        int launched = 0;
+        auto launch = [&](auto kernel, int wc, int wg, int ns) -> int {
+            const dfk::SweepSmem S = dfk::sweep_smem_layout(static_cast<int>(P), N, wc, ns);
+            if (S.total > static_cast<size_t>(ctx->max_smem_optin)) return DFK_OK;  // does not fit: try the next shape
+            DFK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S.total)));
             ProfScope ps(ctx, 0, st);
-            dfk::sweep_period_kernel<<<grid, dfk::kSweepThreads, S.total, st>>>(sp);
+            kernel<<<grid, (wc + wg) * 32, S.total, st>>>(sp);
             ctx->launches++;
             DFK_CUDA(cudaGetLastError());
+            launched = 1;
             return DFK_OK;
+        };
+        int rc = DFK_OK;
+        switch (dev_int("DFK_SWEEP_SHAPE", 610)) {  // consumer warps x 100 + generator warps
+            case 88: rc = launch(dfk::sweep_period_kernel<8, 8, 8>, 8, 8, 8); break;
+            case 79: rc = launch(dfk::sweep_period_kernel<7, 9, 9>, 7, 9, 9); break;
+            case 511: rc = launch(dfk::sweep_period_kernel<5, 11, 11>, 5, 11, 11); break;
+            default: rc = launch(dfk::sweep_period_kernel<6, 10, 10>, 6, 10, 10); break;
         }
+        if (rc) return rc;
+        if (!launched) rc = launch(dfk::sweep_period_kernel<5, 11, 6>, 5, 11, 6);  // many harmonics: a shallower ring
+        if (rc) return rc;
+        if (launched) return DFK_OK;
     }
     // any other geometry: records generated into scratch in waves, then the ordinary lock-in
     const double w0 = 2.0 * dfk::kPi * f_mod / f_samp;

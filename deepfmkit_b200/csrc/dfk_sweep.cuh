@@ -22,12 +22,13 @@ struct SweepParams {
 
 struct SweepSmem {
     PeriodSmem period;   // T, rows (stage / barrier slots unused)
-    size_t off_clean, off_stage, off_x, off_bar, total;
+    size_t off_clean, off_stage, off_x, off_ctr, total;
 };
 
-inline __host__ __device__ SweepSmem sweep_smem_layout(int P, int N) {
+// wc consumer warps (one transposed-combination scratch each), ns stages of eight records
+inline __host__ __device__ SweepSmem sweep_smem_layout(int P, int N, int wc, int ns) {
     SweepSmem S;
-    S.period = period_smem_layout(P, N, 0, kFoldConsumerWarps);
+    S.period = period_smem_layout(P, N, 0, wc);
     size_t o = 0;
     S.period.off_t = o;
     o += static_cast<size_t>(S.period.quarter + 1) * S.period.nrows * 8;
@@ -38,63 +39,61 @@ inline __host__ __device__ SweepSmem sweep_smem_layout(int P, int N) {
     o += static_cast<size_t>(P) * 8;
     o = (o + 15) & ~static_cast<size_t>(15);
     S.off_stage = o;
-    o += static_cast<size_t>(kFoldConsumerWarps) * kPeriodNbw * P * 8;
+    o += static_cast<size_t>(ns) * kPeriodNbw * P * 8;
     S.off_x = o;
-    o += kFoldConsumerWarps * S.period.x_per_warp * 8;
+    o += static_cast<size_t>(wc) * S.period.x_per_warp * 8;
     o = (o + 7) & ~static_cast<size_t>(7);
-    S.off_bar = o;
-    o += static_cast<size_t>(2 * kFoldConsumerWarps) * 8;
+    S.off_ctr = o;
+    o += static_cast<size_t>(2 * ns) * 8;
     S.total = o;
     return S;
 }
 
-// 16 warps: warp w < 8 demodulates the groups that generator warp w + 8 draws for it.  A pair shares one stage of
-// eight records: the generator refills it while its consumer is in the product phase, which reads only the
-// transposed combinations.  Two mbarriers per pair (full / free), one arrival each.
-constexpr int kSweepThreads = 2 * kFoldConsumerWarps * 32;
-
-__global__ void __launch_bounds__(kSweepThreads, 1) sweep_period_kernel(const SweepParams p) {
+// 16 warps: WG generator warps draw groups of eight records into a CTA-wide ring of NS stages, WC consumer warps
+// demodulate them.  Group i of the CTA lives in stage i % NS, is drawn by generator i % WG and demodulated by consumer
+// i % WC; a stage is released right after the combinations are formed (the product reads only the warp's transposed
+// scratch), so it refills during the product.  Successive occupants of a stage belong to different warps on both
+// sides, so the hand-over uses two monotonic counters per stage (groups written, groups released) rather than phase
+// parities.  The generator's integer work is the longer half: 10 generator warps to 6 consumers measured best.
+template <int WC, int WG, int NS>
+__global__ void __launch_bounds__((WC + WG) * 32, 1) sweep_period_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sigma_sh;
     const int P = static_cast<int>(p.synth.P), N = p.N;
-    const SweepSmem S = sweep_smem_layout(P, N);
+    const SweepSmem S = sweep_smem_layout(P, N, WC, NS);
     const PeriodSmem& L = S.period;
     double* T = reinterpret_cast<double*>(smem_raw + L.off_t);
     int* row_type = reinterpret_cast<int*>(smem_raw + L.off_rows);
     int* row_out = row_type + L.nrows;
     double* clean = reinterpret_cast<double*>(smem_raw + S.off_clean);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + S.off_bar);
-    uint64_t* empty = full + kFoldConsumerWarps;
+    volatile unsigned long long* written = reinterpret_cast<volatile unsigned long long*>(smem_raw + S.off_ctr);
+    volatile unsigned long long* released = written + NS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pair = warp & (kFoldConsumerWarps - 1);
-    const bool generator = warp >= kFoldConsumerWarps;
+    const bool generator = warp >= WC;
     constexpr int NBW = kPeriodNbw;
-    if (tid == 0) {
-        sigma_sh = clean_ac_rms(p.synth.amp, p.synth.vis, p.phi, p.synth.m) * p.synth.sigma_scale;
-        for (int w = 0; w < kFoldConsumerWarps; ++w) {
-            mbar_init(&full[w], 1);
-            mbar_init(&empty[w], 1);
-        }
-        mbar_fence_init();
-    }
-    for (int j = tid; j < P; j += kSweepThreads) clean[j] = synth_clean(p.synth, p.phi, j);
-    period_build_tables(P, N, L.nrows, L.quarter, T, row_type, row_out, tid, kSweepThreads);
+    constexpr int kThreads = (WC + WG) * 32;
+    if (tid == 0) sigma_sh = clean_ac_rms(p.synth.amp, p.synth.vis, p.phi, p.synth.m) * p.synth.sigma_scale;
+    if (tid < 2 * NS) written[tid] = 0ull;  // (written and released are contiguous)
+    for (int j = tid; j < P; j += kThreads) clean[j] = synth_clean(p.synth, p.phi, j);
+    period_build_tables(P, N, L.nrows, L.quarter, T, row_type, row_out, tid, kThreads);
     const double sigma = sigma_sh;
-    double* stage = reinterpret_cast<double*>(smem_raw + S.off_stage) + static_cast<size_t>(pair) * NBW * P;
-    double* X = reinterpret_cast<double*>(smem_raw + S.off_x) + pair * L.x_per_warp;
+    double* stage_base = reinterpret_cast<double*>(smem_raw + S.off_stage);
     const int quads = P >> 2;  // P % 4 == 0
     // floor(i / quads) = umulhi(i, ceil(2^32 / quads)) for i < 2^16 (here i < 8 * 64)
     const unsigned quads_magic = static_cast<unsigned>((0x100000000ull + quads - 1) / quads);
     const long long ngroups = (p.nbuf + NBW - 1) / NBW;
-    uint32_t phase = 0;
-    for (long long g = static_cast<long long>(blockIdx.x) * kFoldConsumerWarps + pair; g < ngroups;
-         g += static_cast<long long>(gridDim.x) * kFoldConsumerWarps, phase ^= 1u) {
-        const long long b0 = g * NBW;
-        const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
-        if (generator) {
-            mbar_wait(&empty[pair], phase ^ 1u);  // the first wait passes: nothing to free yet
-            for (int i = lane; i < nb * quads; i += 32) {
-                const int s = static_cast<int>(__umulhi(static_cast<unsigned>(i), quads_magic)), q = i - s * quads;  // i / quads
+    const long long my_groups = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (generator) {
+        for (long long i = warp - WC; i < my_groups; i += WG) {
+            const int st = static_cast<int>(i % NS);
+            const unsigned long long k = static_cast<unsigned long long>(i / NS);  // occupants of the stage before this one
+            const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
+            const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+            double* stage = stage_base + static_cast<size_t>(st) * NBW * P;
+            while (released[st] < k) __nanosleep(32);
+            __threadfence_block();
+            for (int q0 = lane; q0 < nb * quads; q0 += 32) {
+                const int s = static_cast<int>(__umulhi(static_cast<unsigned>(q0), quads_magic)), q = q0 - s * quads;  // q0 / quads
                 double y[4];
                 synth_quad_values<true>(p.synth, 1, clean, p.phi, sigma, p.c0 + b0 + s, q, y);
                 double2* dst = reinterpret_cast<double2*>(stage + s * P + 4 * q);
@@ -102,12 +101,27 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_period_kernel(const Sw
                 dst[1] = make_double2(y[2], y[3]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[pair]);
-        } else {
-            mbar_wait(&full[pair], phase);
+            if (lane == 0) {
+                __threadfence_block();
+                written[st] = k + 1;
+            }
+        }
+    } else {
+        double* X = reinterpret_cast<double*>(smem_raw + S.off_x) + warp * L.x_per_warp;
+        for (long long i = warp; i < my_groups; i += WC) {
+            const int st = static_cast<int>(i % NS);
+            const unsigned long long k = static_cast<unsigned long long>(i / NS);
+            const long long b0 = (blockIdx.x + i * gridDim.x) * NBW;
+            const int nb = static_cast<int>(min(static_cast<long long>(NBW), p.nbuf - b0));
+            const double* stage = stage_base + static_cast<size_t>(st) * NBW * P;
+            while (written[st] <= k) __nanosleep(32);
+            __threadfence_block();
             period_combos(stage, X, P, L.xrow, lane);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[pair]);
+            if (lane == 0) {
+                __threadfence_block();
+                released[st] = k + 1;
+            }
             period_product(X, T, row_type, row_out, P, N, L.nrows, L.xrow, nb, b0, p.qi, p.dc, lane);
             __syncwarp();
         }
