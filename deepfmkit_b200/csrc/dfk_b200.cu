@@ -1448,6 +1448,25 @@ int dfk_probe_fp64(dfk_ctx* ctx, double* tflops_out) {
 int dfk_dev_set(const char* name, int32_t value) {
     if (!name || !*name || std::strlen(name) >= sizeof(g_dev[0].name)) return fail(DFK_ERR_ARG, "bad override name");
     std::lock_guard<std::mutex> lock(g_dev_mutex);
+    // geometry of the staged host copies (dfk_host.h), shared by every translation unit
+    if (std::strcmp(name, "DFK_STAGE_KB") == 0) {
+        if (value < 64 || static_cast<size_t>(value) * 1024 > dfk_ctx::kStageBytes) return fail(DFK_ERR_ARG, "stage size out of range");
+        host_copy_tuning().stage_bytes = static_cast<size_t>(value) * 1024;
+        return DFK_OK;
+    }
+    if (std::strcmp(name, "DFK_STAGERS") == 0) {
+        if (value < 2 || value > dfk_ctx::kStagers) return fail(DFK_ERR_ARG, "stager count out of range");
+        host_copy_tuning().stagers = value;
+        return DFK_OK;
+    }
+    if (std::strcmp(name, "DFK_COPY_NT") == 0) {
+        host_copy_tuning().nt = value != 0;
+        return DFK_OK;
+    }
+    if (std::strcmp(name, "DFK_COPY_THREADS") == 0) {
+        host_copy_tuning().threads = std::max(1, static_cast<int>(value));
+        return DFK_OK;
+    }
     const int n = g_dev_count.load(std::memory_order_relaxed);
     for (int i = 0; i < n; ++i)
         if (std::strcmp(g_dev[i].name, name) == 0) {
@@ -1464,6 +1483,7 @@ int dfk_dev_set(const char* name, int32_t value) {
 void dfk_dev_clear(void) {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
     g_dev_count.store(0, std::memory_order_release);
+    host_copy_tuning() = HostCopyTuning();
 }
 
 int64_t dfk_launch_count(dfk_ctx* ctx) { return ctx ? ctx->launches : 0; }

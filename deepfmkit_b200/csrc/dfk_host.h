@@ -4,9 +4,11 @@
 #include "../../include/dfk_b200.h"
 
 #include <cuda_runtime.h>
+#include <immintrin.h>
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <condition_variable>
@@ -49,10 +51,10 @@ struct dfk_ctx {
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;
     // pageable host records are staged through pinned buffers filled by a few copy threads
-    static constexpr int kStagers = 3;
+    static constexpr int kStagers = 8;               // allocated on first use, as many as HostCopyTuning::stagers
     static constexpr size_t kStageBytes = 64u << 20;
-    void* stager[kStagers] = {nullptr, nullptr, nullptr};
-    cudaEvent_t stager_free[kStagers] = {nullptr, nullptr, nullptr};
+    void* stager[kStagers] = {};
+    cudaEvent_t stager_free[kStagers] = {};
     DevBuf qi, dc, retry, counters, slab[2], rows, stats, stats_part, misc, qi_seed, dc_seed;
     static constexpr int kPostBufs = 8;
     DevBuf post[kPostBufs];  // scratch of the ingest / spectra / generator entries (dfk_post.cu, dfk_ingest.cu)
@@ -208,7 +210,7 @@ public:
 private:
     CopyPool() {
         unsigned hw = std::thread::hardware_concurrency();
-        const int n = static_cast<int>(hw ? std::min(hw, 16u) : 4u) - 1;
+        const int n = static_cast<int>(hw ? std::min(hw, 32u) : 4u) - 1;
         for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
     }
     ~CopyPool() {
@@ -253,9 +255,42 @@ private:
     bool stop_ = false;
 };
 
+// Geometry of the staged copies (development overrides DFK_STAGE_KB, DFK_STAGERS, DFK_COPY_NT, DFK_COPY_THREADS).
+struct HostCopyTuning {
+    size_t stage_bytes = dfk_ctx::kStageBytes;
+    int stagers = 3;
+    int nt = 0;        // 1: non-temporal stores into the stager (no read-for-ownership of its lines)
+    int threads = 16;  // copy threads per stage (the pool holds min(hardware, 32))
+};
+inline HostCopyTuning& host_copy_tuning() {
+    static HostCopyTuning t;
+    return t;
+}
+
+// memcpy with streaming stores; dst 32-byte aligned
+__attribute__((target("avx2"))) inline void stream_copy(char* dst, const char* src, size_t bytes) {
+    size_t i = 0;
+    for (; i + 128 <= bytes; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < bytes) std::memcpy(dst + i, src + i, bytes - i);
+}
+
 inline void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     CopyPool& pool = CopyPool::instance();
-    const int nt = static_cast<int>(std::min<size_t>(static_cast<size_t>(pool.size()), bytes / (4u << 20) + 1));
+    const HostCopyTuning& tune = host_copy_tuning();
+    const int nt = static_cast<int>(
+        std::min<size_t>(static_cast<size_t>(std::min(pool.size(), std::max(1, tune.threads))), bytes / (1u << 20) + 1));
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    const bool streaming = tune.nt && have_avx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
     if (nt <= 1) {
         std::memcpy(dst, src, bytes);
         return;
@@ -263,7 +298,11 @@ inline void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const size_t chunk = ((bytes / nt) + 4095) & ~static_cast<size_t>(4095);
     pool.run(nt, [=](int t) {
         const size_t lo = std::min(bytes, chunk * t), hi = std::min(bytes, chunk * (t + 1));
-        if (hi > lo) std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+        if (hi <= lo) return;
+        if (streaming)
+            stream_copy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+        else
+            std::memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
     });
 }
 
@@ -275,15 +314,16 @@ inline int copy_slab_to_device(dfk_ctx* ctx, void* dst, const void* src, size_t 
         DFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         return DFK_OK;
     }
-    for (int i = 0; i < dfk_ctx::kStagers; ++i) {
+    const HostCopyTuning& tune = host_copy_tuning();
+    for (int i = 0; i < tune.stagers; ++i) {
         if (!ctx->stager[i]) {
             DFK_CUDA(cudaHostAlloc(&ctx->stager[i], dfk_ctx::kStageBytes, cudaHostAllocDefault));
             DFK_CUDA(cudaEventCreateWithFlags(&ctx->stager_free[i], cudaEventDisableTiming));
         }
     }
     int k = 0;
-    for (size_t off = 0; off < bytes; off += dfk_ctx::kStageBytes, k = (k + 1) % dfk_ctx::kStagers) {
-        const size_t n = std::min(dfk_ctx::kStageBytes, bytes - off);
+    for (size_t off = 0; off < bytes; off += tune.stage_bytes, k = (k + 1) % tune.stagers) {
+        const size_t n = std::min(tune.stage_bytes, bytes - off);
         DFK_CUDA(cudaEventSynchronize(ctx->stager_free[k]));  // (a never-recorded event counts as complete)
         parallel_memcpy(ctx->stager[k], static_cast<const char*>(src) + off, n);
         DFK_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off, ctx->stager[k], n, cudaMemcpyHostToDevice, ctx->copy_stream));

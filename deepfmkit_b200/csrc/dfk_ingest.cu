@@ -53,7 +53,7 @@ int parallel_pread(int fd, void* dst, int64_t off, size_t n) {
 }
 
 int ensure_stagers(dfk_ctx* ctx) {
-    for (int i = 0; i < dfk_ctx::kStagers; ++i) {
+    for (int i = 0; i < host_copy_tuning().stagers; ++i) {
         if (!ctx->stager[i]) {
             DFK_CUDA(cudaHostAlloc(&ctx->stager[i], dfk_ctx::kStageBytes, cudaHostAllocDefault));
             DFK_CUDA(cudaEventCreateWithFlags(&ctx->stager_free[i], cudaEventDisableTiming));
@@ -76,8 +76,9 @@ int source_to_device(dfk_ctx* ctx, const ByteSource& src, int64_t src_off, void*
     int rc = ensure_stagers(ctx);
     if (rc) return rc;
     int k = 0;
-    for (size_t off = 0; off < bytes; off += dfk_ctx::kStageBytes, k = (k + 1) % dfk_ctx::kStagers) {
-        const size_t n = std::min(dfk_ctx::kStageBytes, bytes - off);
+    const HostCopyTuning& tune = host_copy_tuning();
+    for (size_t off = 0; off < bytes; off += tune.stage_bytes, k = (k + 1) % tune.stagers) {
+        const size_t n = std::min(tune.stage_bytes, bytes - off);
         DFK_CUDA(cudaEventSynchronize(ctx->stager_free[k]));
         rc = parallel_pread(src.fd, ctx->stager[k], src_off + static_cast<int64_t>(off), n);
         if (rc) return rc;
