@@ -105,23 +105,39 @@ def simulate_asd_batch(trials: np.ndarray, n_samples: int, f_samp: float, tables
     return (y, truth) if with_truth else y
 
 
-def simulate(sim, n_seconds, mode="asd", snr_db=None, trial_num=0, device=0):
+def simulate(sim, n_seconds, mode="asd", snr_db=None, trial_num=0, device=0, witness=None):
     """One channel: ``SignalGenerator.generate(main_config, n_seconds, mode, trial_num, snr_db=...)['main']``
-    (physics.py:380-421) as a ``DeepRawObject`` whose samples live on the device."""
+    (physics.py:380-421) as a ``DeepRawObject`` whose samples live on the device.
+
+    witness: a second ``DFMIObject`` ('asd' mode only, physics.py:458-471).  Returns ``(main, witness)`` then: the
+    witness sees the same noise realisation -- same trial number, noise levels taken from the main channel's laser,
+    as the reference draws one set of noise arrays from ``main_config`` -- through its own static interferometer.
+    Both records come out of one launch."""
     import torch
     from .core import DeepRawObject
     n = int(n_seconds * sim.f_samp)
     sim.N = n
     if mode == "asd":
         tables = WaveformTables(n, sim.f_samp)
-        rec = pack_asd_trial(sim.laser, sim.ifo, sim.f_samp, trial_num, tables, dynamic=True)
-        y, truth = simulate_asd_batch(rec[None, :], n, sim.f_samp, tables, device=device, with_truth=True)
+        recs = [pack_asd_trial(sim.laser, sim.ifo, sim.f_samp, trial_num, tables, dynamic=True)]
+        if witness is not None:
+            w = pack_asd_trial(witness.laser, witness.ifo, sim.f_samp, trial_num, tables, dynamic=False)
+            w[12:14] = recs[0][12:14]
+            recs.append(w)
+        y, truth = simulate_asd_batch(np.stack(recs), n, sim.f_samp, tables, device=device, with_truth=True)
         raw = DeepRawObject(device_data=y[0], f_samp=sim.f_samp, f_mod=sim.laser.f_mod, label=sim.label, sim=sim)
         raw.phi_sim = truth[0]
-        return raw
+        if witness is None:
+            return raw
+        raw_w = DeepRawObject(device_data=y[1], f_samp=witness.f_samp, f_mod=witness.laser.f_mod, label=witness.label,
+                              sim=witness)
+        raw_w.phi_sim = truth[1]
+        return raw, raw_w
     if mode == "snr":
         if snr_db is None:
             raise ValueError("SNR mode requires a value for 'snr_db'.")
+        if witness is not None:  # physics.py:414-415 hands the witness to the 'asd' engine only
+            raise ValueError("witness channels are generated in 'asd' mode only")
         ctx = _lib.get_context(device)
         dev = torch.device("cuda", device)
         y = torch.empty(n, dtype=torch.float64, device=dev)

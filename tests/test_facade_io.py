@@ -1,0 +1,171 @@
+"""The façade's file formats and witness channels (the callers either side of the path).
+
+Fixture tests/golden/facade_io.npz, minted by the unmodified reference: ``fit_data`` text written by the reference's
+``DeepFitObject.to_txt`` with what its ``load_fit`` reads back; ``create_witness_channel`` results; a main + witness
+pair of 'asd'-mode records.  CPU part: ``load_fit`` returns the reference's arrays bit for bit and ``to_txt`` writes
+the reference's bytes.  GPU part (-m gpu): witness simulation against the reference's records (gate 2e-8, as for every
+'asd' record: tests/test_experiment.py), and a raw record written by ``DeepRawObject.to_txt`` read back bit-identically
+by the device text parser.
+"""
+import numpy as np
+import pytest
+
+COLS = ("ssq", "amp", "m", "phi", "psi", "dc")
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _write(tmp_path, g, name):
+    path = tmp_path / f"{name}.txt"
+    path.write_bytes(g[f"fitfile_{name}_text"].tobytes())
+    return str(path)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_load_fit_reads_what_the_reference_reads(golden, tmp_path, name):
+    import deepfmkit_b200 as dfk
+    g = golden("facade_io")
+    path = _write(tmp_path, g, name)
+    dff = dfk.DeepFitFramework()
+    dff.load_fit(path, labels=["x"])
+    hdr = g[f"fitfile_{name}_hdr"]
+    assert [dff.channr, dff.t0, dff.f_samp, dff.f_mod, dff.n, dff.R, dff.fs] == list(hdr)
+    assert isinstance(dff.t0, int) and isinstance(dff.n, int) and isinstance(dff.R, int)
+    fit = dff.fits["x"]
+    cols = g[f"fitfile_{name}_cols"]
+    for c, ref in zip(COLS, cols):
+        assert np.array_equal(getattr(fit, c), ref), c  # bit for bit
+    assert np.array_equal(fit.time, g[f"fitfile_{name}_time"])
+    assert fit.nbuf == cols.shape[1] and fit.label == "x"
+    assert (fit.n, fit.R, fit.fs, fit.ndata, fit.init_a, fit.init_m) == (dff.n, dff.R, dff.fs, 10, 1.6, 6.0)
+    # default labels: the reference needs a raw file name there; without one the fit file's is used
+    dff2 = dfk.DeepFitFramework(fit_file=path)
+    assert list(dff2.fits) == [path + "_ch0"]
+    fresh = dfk.core.DeepFitObject()
+    fresh.fit_file = path
+    fresh.parse_header()
+    assert [fresh.t0, fresh.f_samp, fresh.f_mod, fresh.n, fresh.R, fresh.fs] == list(hdr[1:])
+
+
+def test_to_txt_writes_the_reference_bytes(golden, tmp_path):
+    import deepfmkit_b200 as dfk
+    g = golden("facade_io")
+    # (a) load, then write: the framework's defaults for init_a / init_m go into the header as in the reference
+    path = _write(tmp_path, g, "a")
+    dff = dfk.DeepFitFramework()
+    dff.load_fit(path, labels=["t"])
+    dff.to_txt(str(tmp_path) + "/out_")
+    assert (tmp_path / "out_t.txt").read_bytes() == g["fitfile_a_text"].tobytes()
+    dff.to_txt(str(tmp_path) + "/sel_", labels=["t"])
+    assert (tmp_path / "sel_t.txt").read_bytes() == g["fitfile_a_text"].tobytes()
+    # (b) a fit object as DeepFitFramework.fit leaves it (init_a = init_m = 0, integer t0)
+    n, R, fs, init_a, init_m, t0, f_samp, f_mod = g["fitfile_b_scalars"]
+    fit = dfk.core.DeepFitObject()
+    fit.n, fit.R, fit.fs, fit.init_a, fit.init_m = int(n), int(R), float(fs), int(init_a), int(init_m)
+    fit.t0, fit.f_samp, fit.f_mod = int(t0), float(f_samp), int(f_mod)
+    for c, ref in zip(COLS, g["fitfile_b_cols"]):
+        setattr(fit, c, ref)
+    out = tmp_path / "b_out.txt"
+    fit.to_txt(str(out))
+    assert out.read_bytes() == g["fitfile_b_text"].tobytes()
+
+
+def test_create_witness_channel_matches_reference(golden):
+    import deepfmkit_b200 as dfk
+    from deepfmkit_b200 import physics
+    g = golden("facade_io")
+    df, wavelength, psi, f_mod = g["wit_laser"]
+    laser = physics.LaserConfig(psi=psi)
+    laser.df, laser.wavelength, laser.f_mod = df, wavelength, f_mod
+    ifo = physics.InterferometerConfig()
+    ifo.ref_arml, ifo.meas_arml, ifo.phi, ifo.arml_mod_amp, ifo.arml_mod_f, ifo.arml_mod_psi = g["wit_main_ifo"]
+    main = physics.DFMIObject("main", laser, ifo, f_samp=200e3)
+    main.fit_n = 10
+    dff = dfk.DeepFitFramework()
+    dff.load_sim(main)
+    for (label, kw), ref in zip((("w_default", {}), ("w_m", {"m_witness": 0.07}), ("w_dl", {"delta_l_witness": 2.5e-3})),
+                                g["wit_configs"]):
+        w = dff.create_witness_channel("main", label, **kw)
+        got = [w.ifo.ref_arml, w.ifo.meas_arml, w.ifo.phi, w.m, w.fit_n, w.f_samp, w.ifo.arml_mod_amp]
+        assert np.allclose(got, ref, rtol=1e-15, atol=0), (label, got, list(ref))
+        assert w.laser is laser and dff.sims[label] is w
+    with pytest.raises(KeyError):
+        dff.create_witness_channel("nope", "w")
+    with pytest.raises(ValueError):
+        dff.create_witness_channel("main", "w", m_witness=0.1, delta_l_witness=1e-3)
+    laser.df = 0
+    with pytest.raises(ValueError):
+        dff.create_witness_channel("main", "w")
+    assert dff.new_sim("fresh") == "fresh" and dff.sims["fresh"].m > 0
+    assert len(dff.new_sim()) == 15  # time-stamp label
+
+
+def _main_and_witness(g):
+    import deepfmkit_b200 as dfk
+    from deepfmkit_b200 import physics
+    df, wavelength, psi, f_mod = g["wit_laser"]
+    laser = physics.LaserConfig(psi=psi)
+    laser.df, laser.wavelength, laser.f_mod = df, wavelength, f_mod
+    ifo = physics.InterferometerConfig()
+    ifo.ref_arml, ifo.meas_arml, ifo.phi, ifo.arml_mod_amp, ifo.arml_mod_f, ifo.arml_mod_psi = g["wit_main_ifo"]
+    dff = dfk.DeepFitFramework()
+    dff.load_sim(physics.DFMIObject("main", laser, ifo, f_samp=200e3))
+    dff.create_witness_channel("main", "w_m", m_witness=0.07)
+    return dff
+
+
+@pytest.mark.gpu
+def test_witness_simulation_matches_reference(torch_mod, golden):
+    g = golden("facade_io")
+    dff = _main_and_witness(g)
+    dff.simulate("main", 0.02, mode="asd", witness_label="w_m", trial_num=0)
+    assert set(dff.raws) == {"main", "w_m"}
+    for key, label in (("main", "main"), ("wit", "w_m")):
+        raw = dff.raws[label]
+        y = raw.data.values.flatten()
+        ref = g[f"wit_{key}_data"]
+        assert y.shape == ref.shape and np.max(np.abs(y - ref)) < 2e-8, (label, np.max(np.abs(y - ref)))
+        truth = raw.phi_sim.cpu().numpy()
+        assert np.max(np.abs(truth - g[f"wit_{key}_phi_sim"])) <= 4e-15 * max(1.0, np.max(np.abs(truth))), label
+        assert raw.sim is dff.sims[label] and raw.f_mod == dff.sims[label].laser.f_mod
+    # the witness shares the main channel's noise realisation: with white amplitude noise switched on, the two
+    # records' deviations from their noise-free selves are the same multiplicative factor
+    dff.sims["main"].laser.amp_n = 1e-4
+    clean_main, clean_wit = dff.raws["main"].data.values.flatten(), dff.raws["w_m"].data.values.flatten()
+    dff.simulate("main", 0.02, mode="asd", witness_label="w_m", trial_num=7)
+    rm = dff.raws["main"].data.values.flatten() / clean_main
+    rw = dff.raws["w_m"].data.values.flatten() / clean_wit
+    assert np.std(rm) > 1e-3 and np.max(np.abs(rm - rw)) < 1e-9
+    # 'snr' mode generates the main channel only, as the reference's engine does
+    dff.raws.clear()
+    dff.simulate("main", 0.01, mode="snr", snr_db=30.0, witness_label="w_m")
+    assert set(dff.raws) == {"main"}
+
+
+@pytest.mark.gpu
+def test_raw_to_txt_round_trips_through_the_device_parser(torch_mod, tmp_path):
+    import deepfmkit_b200 as dfk
+    rng = np.random.RandomState(4)
+    x = np.concatenate([rng.randn(3000) * 10.0 ** rng.randint(-8, 8, 3000), [0.0, -0.0, 1e-300, 1.7976931348623157e308]])
+    raw = dfk.DeepRawObject(data=x, f_samp=200000.0, f_mod=1000.0, label="r", t0=20240131120000)
+    path = str(tmp_path / "raw.txt")
+    raw.to_txt(path)
+    dff = dfk.DeepFitFramework(raw_file=path, raw_labels=["back"])
+    back = dff.raws["back"]
+    assert (dff.channr, dff.t0, dff.f_samp, dff.f_mod) == (1, 20240131120000, 200000.0, 1000.0)
+    got = back.data.values.flatten()
+    # the device parser reproduces pandas' reader bit for bit (the oracle restates it); that reader is not correctly
+    # rounded -- it can lose ~1e-12 on fixed-notation numbers with leading zeros -- hence the looser gate to the input
+    from oracle import ingest_oracle as io_orc
+    _, vals = io_orc.load_raw(path)
+    assert got.shape == x.shape and np.array_equal(got, np.asarray(vals).reshape(-1))
+    assert np.allclose(got, x, rtol=1e-11, atol=0)
+    again = dfk.DeepRawObject()
+    again.raw_file = path
+    again.parse_header()
+    assert (again.t0, again.f_samp, again.f_mod) == (20240131120000, 200000.0, 1000.0)
