@@ -14,6 +14,33 @@ def second_harmonic_distortion(t_phase, distortion_amp=0.0, distortion_phase=0.0
     return np.cos(t_phase) + distortion_amp * np.cos(2 * t_phase + distortion_phase)
 
 
+def triangle_wave(t_phase, width=0.5):
+    """Sawtooth of period 2 pi rising from -1 to 1 over the fraction ``width`` of the period and falling back over the
+    rest; 0.5 gives the symmetric triangle (waveforms.py:26-32, where a signal-processing library supplies it).
+    Table-evaluated."""
+    t = np.asarray(t_phase, dtype=np.float64)
+    w = float(width)
+    if not 0.0 <= w <= 1.0:
+        raise ValueError("width must be in the interval [0, 1].")
+    tmod = np.mod(t, 2 * np.pi)
+    y = np.empty_like(tmod)
+    rising = tmod < w * 2 * np.pi
+    if w > 0:
+        y[rising] = tmod[rising] / (np.pi * w) - 1
+    if w < 1:
+        y[~rising] = (np.pi * (w + 1) - tmod[~rising]) / (np.pi * (1 - w))
+    return y
+
+
+def square_wave(t_phase, duty=0.5):
+    """+1 for the first ``duty`` fraction of each 2 pi period, -1 for the rest (waveforms.py:34-43).  Table-evaluated."""
+    t = np.asarray(t_phase, dtype=np.float64)
+    d = float(duty)
+    if not 0.0 <= d <= 1.0:
+        raise ValueError("duty must be in the interval [0, 1].")
+    return np.where(np.mod(t, 2 * np.pi) < d * 2 * np.pi, 1.0, -1.0)
+
+
 def dfm_like_wave(t_phase, harmonics=None):
     """Fundamental plus in-phase harmonics ``{n: amplitude}`` (waveforms.py:47-64)."""
     if harmonics is None:

@@ -8,6 +8,9 @@ facade_io.npz holds
   * fitfile_*: the text the reference's own ``DeepFitObject.to_txt`` (data.py:180-213) writes for (a) the first rows
     of the reference's test record ``test/fit_data.txt`` as its ``load_fit`` (core.py:288-332) read them, and (b) a
     fit of a simulated record; beside each text, the arrays and header fields ``load_fit`` returns for it;
+  * help_*: ``helpers.py`` (CRLB, SNR -> noise density, Jacobian, m precision), the sawtooth / square waveforms, the
+    W-DFMI and amplitude-offset factories, ``workers.py`` (ambiguity point, ``run_efficiency_trial`` and
+    ``run_single_trial`` on noise-free 'asd' records);
   * wit_*: ``create_witness_channel`` (core.py:519-588) for three ways of asking, and a noise-free main + witness
     pair of records from ``simulate(..., witness_label=...)`` in 'asd' mode with the ground-truth phases.
 """
@@ -83,11 +86,67 @@ def witness_cases(out):
         out[f"wit_{key}_phi_sim"] = np.asarray(raw.phi_sim, dtype=float)
 
 
+def helper_cases(out):
+    from DeepFMKit import factories as rfac
+    from DeepFMKit import helpers as rh
+    from DeepFMKit import waveforms as rw
+    from DeepFMKit import workers as rwork
+    crlb_in = [(6.0, 10, 40.0, 4000), (2.0, 15, 40.0, 200), (20.0, 15, 30.0, 200), (11.3, 30, 20.0, 1000)]
+    out["help_crlb_in"] = np.array(crlb_in)
+    out["help_crlb"] = np.array([rh.calculate_crlb_for_m(m, int(n), s, int(R)) for m, n, s, R in crlb_in])
+    out["help_asd"] = np.array([rh.snr_to_asd(40.0, 200e3), rh.snr_to_asd(17.5, 1e6)])
+    out["help_jac"] = np.stack([rh.calculate_jacobian(10, np.array(p)) for p in ([1.3, 6.2, 0.4, -0.2], [0.0, 3.0, 1.0, 0.5])])
+    out["help_mprec"] = rh.calculate_m_precision(np.array([2.0, 5.5, 9.0, 14.0]), 12, 35.0)
+    laser, ifo = core.LaserConfig(), core.InterferometerConfig()
+    ifo.ref_arml, ifo.meas_arml = 0.25, 0.1
+    rh.set_laser_df_for_effect(laser, ifo, 7.7)
+    out["help_df"] = np.array([laser.df])
+    t = np.linspace(-15.0, 40.0, 5001)
+    out["help_wave_t"] = t
+    out["help_wave_tri"] = np.stack([rw.triangle_wave(t), rw.triangle_wave(t, width=0.2), rw.triangle_wave(t, width=1.0)])
+    out["help_wave_sq"] = np.stack([rw.square_wave(t), rw.square_wave(t, duty=0.3)])
+    # factories
+    fw = rfac.StandardWDFMIExperimentFactory(rw.second_harmonic_distortion, opd_main=0.25)
+    cfg = fw({"m_main": 8.0, "m_witness": 0.09, "psi": 0.2, "phi": 0.6, "distortion_amp": 0.05, "distortion_phase": 0.3})
+    l, mi, wi = cfg["laser_config"], cfg["main_ifo_config"], cfg["witness_ifo_config"]
+    out["help_fac_w"] = np.array([l.df, l.psi, mi.ref_arml, mi.meas_arml, mi.phi, wi.ref_arml, wi.meas_arml, wi.phi,
+                                  l.waveform_kwargs["distortion_amp"], l.waveform_kwargs["distortion_phase"]])
+    cfg0 = fw({"m_main": 8.0})
+    out["help_fac_w0"] = np.array([cfg0["witness_ifo_config"].ref_arml, cfg0["witness_ifo_config"].meas_arml,
+                                   cfg0["witness_ifo_config"].phi])
+    out["help_fac_w_keys"] = np.array(sorted(fw._get_expected_params_keys()))
+    fa = rfac.VairableAmplitudeOffset(opd_main=0.15)
+    cfga = fa({"m_main": 5.0, "nominal_amplitude": 1.2, "amplitude_offset": -0.15})
+    out["help_fac_a"] = np.array([cfga["laser_config"].amp, cfga["laser_config"].df, cfga["main_ifo_config"].ref_arml,
+                                  cfga["main_ifo_config"].meas_arml])
+    out["help_fac_a_keys"] = np.array(sorted(fa._get_expected_params_keys()))
+    # workers
+    out["help_ambiguity"] = np.array([rwork.calculate_ambiguity_boundary_point(
+        {"delta_f": 3e9, "delta_l": 1e-6, "f0": 2.8e14, "grid_i": 3, "grid_j": 4})[2]])
+    eff_in = [(4.0, 15, 0.001, 0.3), (9.5, 15, 0.002, 1.2), (17.0, 20, 0.001, -0.8)]
+    eff = []
+    for m, nd, secs, phi in eff_in:
+        laser, ifo = core.LaserConfig(), core.InterferometerConfig()
+        ifo.phi = phi
+        rh.set_laser_df_for_effect(laser, ifo, m)
+        eff.append(rwork.run_efficiency_trial({"laser_config": laser, "ifo_config": ifo, "n_seconds": secs, "ndata": nd,
+                                               "m_true": m, "trial_num": 2}))
+    out["help_eff_in"] = np.array(eff_in)
+    out["help_eff_m"] = np.array(eff)
+    laser, ifo = core.LaserConfig(psi=0.1), core.InterferometerConfig()
+    ifo.phi = 0.5
+    rh.set_laser_df_for_effect(laser, ifo, 6.0)
+    fobj = rwork.run_single_trial(laser, ifo, "nls", {"n": 5, "ndata": 12}, n_seconds=0.05, trial_num=1)
+    out["help_single"] = np.stack([fobj.amp, fobj.m, fobj.phi, fobj.psi, fobj.dc, fobj.ssq])
+    out["help_single_scalars"] = np.array([fobj.n, fobj.R, fobj.fs, fobj.nbuf, laser.df])
+
+
 if __name__ == "__main__":
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         fit_file_cases(out, tmp)
     witness_cases(out)
+    helper_cases(out)
     path = os.path.join(HERE, "facade_io.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()})

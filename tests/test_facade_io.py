@@ -169,3 +169,80 @@ def test_raw_to_txt_round_trips_through_the_device_parser(torch_mod, tmp_path):
     again.raw_file = path
     again.parse_header()
     assert (again.t0, again.f_samp, again.f_mod) == (20240131120000, 200000.0, 1000.0)
+
+
+# ------------------------------------------------------------------------ helpers, waveforms, factories, workers
+def test_helpers_match_reference(golden):
+    from deepfmkit_b200 import helpers, physics
+    g = golden("facade_io")
+    got = np.array([helpers.calculate_crlb_for_m(m, int(n), s, int(R)) for m, n, s, R in g["help_crlb_in"]])
+    assert np.allclose(got, g["help_crlb"], rtol=1e-9, atol=0)
+    assert np.allclose([helpers.snr_to_asd(40.0, 200e3), helpers.snr_to_asd(17.5, 1e6)], g["help_asd"], rtol=1e-15)
+    for p, ref in zip(([1.3, 6.2, 0.4, -0.2], [0.0, 3.0, 1.0, 0.5]), g["help_jac"]):
+        jac = helpers.calculate_jacobian(10, np.array(p))
+        assert jac.shape == ref.shape and np.max(np.abs(jac - ref)) < 1e-14
+    got = helpers.calculate_m_precision(np.array([2.0, 5.5, 9.0, 14.0]), 12, 35.0)
+    assert np.allclose(got, g["help_mprec"], rtol=1e-9, atol=0)
+    laser, ifo = physics.LaserConfig(), physics.InterferometerConfig()
+    ifo.ref_arml, ifo.meas_arml = 0.25, 0.1
+    helpers.set_laser_df_for_effect(laser, ifo, 7.7)
+    assert np.isclose(laser.df, g["help_df"][0], rtol=1e-15, atol=0)
+
+
+def test_waveforms_and_factories_match_reference(golden):
+    from deepfmkit_b200 import factories, waveforms
+    g = golden("facade_io")
+    t = g["help_wave_t"]
+    tri = np.stack([waveforms.triangle_wave(t), waveforms.triangle_wave(t, width=0.2), waveforms.triangle_wave(t, width=1.0)])
+    sq = np.stack([waveforms.square_wave(t), waveforms.square_wave(t, duty=0.3)])
+    assert np.array_equal(tri, g["help_wave_tri"]) and np.array_equal(sq, g["help_wave_sq"])
+    assert waveforms.harmonic_terms(waveforms.triangle_wave, {}) is None  # shipped as a table, never guessed at
+    fw = factories.StandardWDFMIExperimentFactory(waveforms.second_harmonic_distortion, opd_main=0.25)
+    cfg = fw({"m_main": 8.0, "m_witness": 0.09, "psi": 0.2, "phi": 0.6, "distortion_amp": 0.05, "distortion_phase": 0.3})
+    l, mi, wi = cfg["laser_config"], cfg["main_ifo_config"], cfg["witness_ifo_config"]
+    got = [l.df, l.psi, mi.ref_arml, mi.meas_arml, mi.phi, wi.ref_arml, wi.meas_arml, wi.phi,
+           l.waveform_kwargs["distortion_amp"], l.waveform_kwargs["distortion_phase"]]
+    assert np.allclose(got, g["help_fac_w"], rtol=1e-15, atol=0)
+    w0 = fw({"m_main": 8.0})["witness_ifo_config"]
+    assert np.allclose([w0.ref_arml, w0.meas_arml, w0.phi], g["help_fac_w0"], rtol=0, atol=0)
+    assert sorted(fw._get_expected_params_keys()) == list(g["help_fac_w_keys"])
+    fa = factories.VairableAmplitudeOffset(opd_main=0.15)
+    cfga = fa({"m_main": 5.0, "nominal_amplitude": 1.2, "amplitude_offset": -0.15})
+    got = [cfga["laser_config"].amp, cfga["laser_config"].df, cfga["main_ifo_config"].ref_arml, cfga["main_ifo_config"].meas_arml]
+    assert np.allclose(got, g["help_fac_a"], rtol=1e-15, atol=0)
+    assert sorted(fa._get_expected_params_keys()) == list(g["help_fac_a_keys"])
+    with pytest.raises(TypeError):
+        factories.StandardWDFMIExperimentFactory("not callable")
+    with pytest.raises(ValueError):
+        factories.VairableAmplitudeOffset(opd_main=0)({"m_main": 1.0, "nominal_amplitude": 1.0, "amplitude_offset": 0.0})
+
+
+def test_ambiguity_point_matches_reference(golden):
+    from deepfmkit_b200 import workers
+    g = golden("facade_io")
+    i, j, v = workers.calculate_ambiguity_boundary_point({"delta_f": 3e9, "delta_l": 1e-6, "f0": 2.8e14, "grid_i": 3, "grid_j": 4})
+    assert (i, j) == (3, 4) and np.isclose(v, g["help_ambiguity"][0], rtol=1e-15, atol=0)
+    assert workers.calculate_ambiguity_boundary_point({"delta_f": 0, "delta_l": 1e-6, "f0": 1.0, "grid_i": 0, "grid_j": 0})[2] == float("inf")
+
+
+@pytest.mark.gpu
+def test_trial_workers_match_reference(torch_mod, golden):
+    from deepfmkit_b200 import helpers, physics, workers
+    g = golden("facade_io")
+    for (m, nd, secs, phi), ref in zip(g["help_eff_in"], g["help_eff_m"]):
+        laser, ifo = physics.LaserConfig(), physics.InterferometerConfig()
+        ifo.phi = phi
+        helpers.set_laser_df_for_effect(laser, ifo, m)
+        got = workers.run_efficiency_trial({"laser_config": laser, "ifo_config": ifo, "n_seconds": secs, "ndata": int(nd),
+                                            "m_true": m, "trial_num": 2})
+        assert abs(got - ref) < 1e-7, (m, got, ref)  # records agree to 2e-8 (running-sum order); m follows
+    laser, ifo = physics.LaserConfig(psi=0.1), physics.InterferometerConfig()
+    ifo.phi = 0.5
+    helpers.set_laser_df_for_effect(laser, ifo, 6.0)
+    fobj = workers.run_single_trial(laser, ifo, "nls", {"n": 5, "ndata": 12}, n_seconds=0.05, trial_num=1)
+    n, R, fs, nbuf, df = g["help_single_scalars"]
+    assert (fobj.n, fobj.R, fobj.fs, fobj.nbuf) == (int(n), int(R), fs, int(nbuf)) and laser.df == df
+    got = np.stack([fobj.amp, fobj.m, fobj.phi, fobj.psi, fobj.dc, fobj.ssq])
+    ref = g["help_single"]
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got[:5] - ref[:5])) < 1e-7 and np.max(np.abs(got[5] - ref[5])) < 1e-9
