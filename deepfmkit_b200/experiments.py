@@ -176,8 +176,8 @@ class Experiment:
                 df_of[counter] = hit[1]
                 continue
             cfg = self.config_factory(params)
-            if "witness_ifo_config" in cfg:
-                raise NotImplementedError("witness channels belong to the W-DFMI fitters, which are outside this package")
+            # a 'witness_ifo_config' (the W-DFMI factory) is simulated by the reference beside the main channel and read by
+            # its W-DFMI fitters only; the analyses run here ('nls', 'ekf': checked above) never look at it
             laser, ifo = cfg["laser_config"], cfg["main_ifo_config"]
             if f_mod is None:
                 f_mod = laser.f_mod

@@ -246,3 +246,26 @@ def test_trial_workers_match_reference(torch_mod, golden):
     ref = g["help_single"]
     assert got.shape == ref.shape
     assert np.max(np.abs(got[:5] - ref[:5])) < 1e-7 and np.max(np.abs(got[5] - ref[5])) < 1e-9
+
+
+@pytest.mark.gpu
+def test_experiment_accepts_the_wdfmi_factory_for_gpu_analyses(torch_mod):
+    """The W-DFMI factory adds a witness interferometer; 'nls' / 'ekf' analyses read the main channel only, so the
+    study gives what the plain DFMI factory gives (experiments.py:46-76)."""
+    import deepfmkit_b200 as dfk
+    from deepfmkit_b200 import factories, waveforms
+    out = []
+    for fac in (factories.StandardWDFMIExperimentFactory, factories.StandardDFMIExperimentFactory):
+        exp = dfk.Experiment("w")
+        exp.set_config_factory(fac(waveforms.second_harmonic_distortion, opd_main=0.2))
+        exp.add_axis("m_main", np.array([5.0, 7.0]))
+        exp.set_static({"m_witness": 0.1} if fac is factories.StandardWDFMIExperimentFactory else {})
+        exp.n_trials = 2
+        exp.n_fit_buffers_per_trial = 5
+        exp.add_analysis("nls", "nls", fitter_kwargs={"ndata": 12})
+        out.append(exp.run())
+    a, b = (o["nls"]["m"]["all_trials"] for o in out)
+    assert np.array_equal(a, b) and np.all(np.abs(a - np.array([5.0, 7.0])[:, None]) < 1e-2)  # ('asd' physics: m to ~1e-3)
+    exp.add_analysis("w", "wdfmi_ortho")
+    with pytest.raises(NotImplementedError):
+        exp.run()
