@@ -3,6 +3,8 @@ experiment factories written for the reference run unchanged.  Only the containe
 is the device generator (csrc/dfk_asd.cuh for 'asd' mode, csrc/dfk_synth.cuh for 'snr' mode)."""
 from __future__ import annotations
 
+import logging
+
 import numpy as np
 
 SPEED_OF_LIGHT = 299792458.0  # speed of light in m/s, the exact SI value the reference uses
@@ -59,3 +61,37 @@ class DFMIObject:
         if delta_l == 0:
             return 0.0
         return 2 * np.pi * self.laser.df * delta_l / SPEED_OF_LIGHT
+
+    def info(self):
+        """Log a summary of the channel (physics.py:297-325)."""
+        opd = self.ifo.meas_arml - self.ifo.ref_arml
+        logging.info(
+            f"\nDFMI channel '{self.label}'\n"
+            f"  laser '{self.laser.label}': wavelength {self.laser.wavelength * 1e6:.3f} um, f_mod {self.laser.f_mod} Hz, "
+            f"df {self.laser.df / 1e9:.3f} GHz, amplitude {self.laser.amp:.2f}, visibility {self.laser.visibility:.2f}\n"
+            f"  interferometer '{self.ifo.label}': arms {self.ifo.ref_arml:.4f} / {self.ifo.meas_arml:.4f} m, "
+            f"OPD {opd * 100:.2f} cm, motion {self.ifo.arml_mod_amp * 1e9:.2f} nm\n"
+            f"  m {self.m:.4f} rad, f_samp {self.f_samp / 1e3:.1f} kHz, fit_n {self.fit_n}, output rate {self.f_fit} Hz, "
+            f"simtime {self.simtime if self.simtime else 'N/A'}, N {self.N if self.N > 0 else 'N/A'}\n")
+
+
+class SignalGenerator:
+    """The reference's physics engine by name (physics.py:362-421): ``generate`` returns the records keyed 'main' and
+    'witness', produced by the device generators (simulation.py).  Pre-computed noise arrays (``external_noise``) are
+    a host-side injection the device generator has no input for: asking for them raises."""
+
+    def generate(self, main_config, n_seconds, mode="asd", trial_num=0, witness_config=None, snr_db=None,
+                 external_noise=None):
+        from .simulation import simulate
+        if mode == "asd":
+            if external_noise:
+                raise NotImplementedError("external noise arrays are not taken by the device generator")
+            out = simulate(main_config, n_seconds, mode="asd", trial_num=trial_num, witness=witness_config)
+            return {"main": out[0], "witness": out[1]} if witness_config is not None else {"main": out}
+        if mode == "snr":
+            if snr_db is None:
+                logging.error("SNR mode requires a value for 'snr_db'.")
+                return {}
+            return {"main": simulate(main_config, n_seconds, mode="snr", snr_db=snr_db, trial_num=trial_num)}
+        logging.error(f"Unknown simulation mode: '{mode}'")
+        return {}

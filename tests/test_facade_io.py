@@ -141,6 +141,14 @@ def test_witness_simulation_matches_reference(torch_mod, golden):
     rm = dff.raws["main"].data.values.flatten() / clean_main
     rw = dff.raws["w_m"].data.values.flatten() / clean_wit
     assert np.std(rm) > 1e-3 and np.max(np.abs(rm - rw)) < 1e-9
+    # the engine under its own name
+    from deepfmkit_b200 import physics
+    chans = physics.SignalGenerator().generate(dff.sims["main"], 0.02, mode="asd", trial_num=7, witness_config=dff.sims["w_m"])
+    assert set(chans) == {"main", "witness"}
+    assert np.array_equal(chans["witness"].data.values, dff.raws["w_m"].data.values)
+    assert physics.SignalGenerator().generate(dff.sims["main"], 0.02, mode="snr") == {}
+    assert physics.SignalGenerator().generate(dff.sims["main"], 0.02, mode="nope") == {}
+    dff.sims["main"].info()
     # 'snr' mode generates the main channel only, as the reference's engine does
     dff.raws.clear()
     dff.simulate("main", 0.01, mode="snr", snr_db=30.0, witness_label="w_m")
