@@ -16,9 +16,9 @@ from ._build import LIB_PATH
 
 ROW_STRIDE = 8
 MAX_HARMONICS = 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 PROFILE_KINDS = 4
-ASD_TRIAL_DOUBLES = 35
+ASD_TRIAL_DOUBLES = 37
 TRIAL_STATS_DOUBLES = 6
 SCHED_INDEPENDENT = 0   # every buffer a cold start from init
 SCHED_EACH = -1         # every buffer its own chunk, seeded from buffer 0 (pool schedule at n_cores >= nbuf - 1)
@@ -106,6 +106,7 @@ SYMBOLS = {
     "dfk_ingest_binary_host": (ctypes.c_int, [_vp, _vp, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_ingest_binary_file": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64, _i32, _i64, _i64, _i32, _d, _d, _vp, _i64]),
     "dfk_synth_asd_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _vp, _i64, _vp, _i64, _vp]),
+    "dfk_synth_asd_noise_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _d, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "dfk_trial_stats_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _vp]),
     "dfk_downsample_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "dfk_downsample_host": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
@@ -422,6 +423,16 @@ class Context:
     def synth_asd_dev(self, trials_ptr, ntrials, N, f_samp, y_ptr, ld, tables_ptr=None, ntables=0, truth_ptr=None):
         _check(self.lib, self.lib.dfk_synth_asd_dev(self._h, trials_ptr, int(ntrials), int(N), float(f_samp), tables_ptr,
                                                     int(ntables), y_ptr, int(ld), truth_ptr))
+
+    NOISE_KEYS = ("laser_frequency", "amplitude", "df", "armlength")  # DFK_NOISE_* order
+
+    def synth_asd_noise_dev(self, trials_ptr, ntrials, N, f_samp, y_ptr, ld, noise_ptrs, noise_rows, tables_ptr=None,
+                            ntables=0, truth_ptr=None):
+        """noise_ptrs: four device pointers (or None) in NOISE_KEYS order, each ``noise_rows x N`` doubles."""
+        arr = (ctypes.c_void_p * 4)(*[p if p else None for p in noise_ptrs])
+        _check(self.lib, self.lib.dfk_synth_asd_noise_dev(self._h, trials_ptr, int(ntrials), int(N), float(f_samp),
+                                                          tables_ptr, int(ntables), arr, int(noise_rows), y_ptr, int(ld),
+                                                          truth_ptr))
 
     def trial_stats_dev(self, values_ptr, npoints, ntrials, ncols, col_stride, out_ptr, center_ptr=None):
         _check(self.lib, self.lib.dfk_trial_stats_dev(self._h, values_ptr, int(npoints), int(ntrials), int(ncols),

@@ -6,7 +6,10 @@
 //   Phi(t)      = w0 ((tau_m + tau_dl) - tau_r) + interp(t - tau_m - tau_dl) - interp(t - tau_r)
 //   y(t)        = (A + n_amp(t)) (1 + C cos Phi(t))
 // with n_df, n_amp white, sigma = asd sqrt(fs / 2) (physics.py:591-597).  The coloured sources (laser frequency and
-// arm-length noise, generated by the third-party pyplnoise in the reference) are not available here.
+// arm-length noise) come from the third-party pyplnoise in the reference and are not generated here; like the
+// reference's engine (generate(..., external_noise=...), physics.py:430-434) the kernel takes pre-computed noise series
+// for all four sources instead -- laser frequency n_f(t) (w0 -> 2 pi (f0 + n_f)), amplitude, df and, on a dynamic
+// channel, arm length (added to the path) -- which then replace the internal draws.
 // One CTA per trial: block-wide prefix sum of the frequency waveform into an L2-resident scratch row, then the
 // delayed-time interpolation np.interp performs, sample by sample.
 #pragma once
@@ -31,8 +34,10 @@ struct AsdTrial {  // one Monte-Carlo trial, 26 doubles
     double nterms;               // > 0: g = sum_k a_k cos(h_k theta + p_k);  0: g from the waveform table
     double table;                // waveform table row when nterms == 0
     double term[kAsdTerms][3];   // h_k, a_k, p_k   (only the first nterms)
+    double dynamic;              // != 0: the channel's arm moves (takes the external arm-length noise)
+    double noise_row;            // >= 0: row of the external noise series this trial reads; < 0: internal white noise
 };
-static_assert(sizeof(AsdTrial) == (17 + 3 * kAsdTerms) * sizeof(double), "AsdTrial layout");
+static_assert(sizeof(AsdTrial) == (19 + 3 * kAsdTerms) * sizeof(double), "AsdTrial layout");
 
 struct AsdParams {
     const AsdTrial* trials;
@@ -45,6 +50,11 @@ struct AsdParams {
     double* y;              // [ntrials][ld]
     long long ld;
     double* truth;          // optional [ntrials][ld]: ground-truth phase w0 ((tau_m + tau_dl) - tau_r)
+    // external noise series [rows][N], each optional: laser frequency, amplitude, df, arm length (physics.py:430-434)
+    const double* ext_fn;
+    const double* ext_amp;
+    const double* ext_df;
+    const double* ext_arm;
 };
 
 DFK_D double asd_waveform(const AsdTrial& tr, const AsdParams& P, long long i) {
@@ -79,8 +89,15 @@ __global__ void __launch_bounds__(kAsdThreads) synth_asd_kernel(const AsdParams 
     __shared__ double carry_sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long j = blockIdx.x; j < P.ntrials; j += gridDim.x) {
-        const AsdTrial tr = P.trials[j];
+        AsdTrial tr = P.trials[j];
         const unsigned long long key = static_cast<unsigned long long>(tr.seed);
+        const bool ext = tr.noise_row >= 0.0;
+        const long long erow = ext ? static_cast<long long>(tr.noise_row) * P.N : 0;
+        const double* e_fn = ext && P.ext_fn ? P.ext_fn + erow : nullptr;
+        const double* e_amp = ext && P.ext_amp ? P.ext_amp + erow : nullptr;
+        const double* e_df = ext && P.ext_df ? P.ext_df + erow : nullptr;
+        const double* e_arm = ext && P.ext_arm && tr.dynamic != 0.0 ? P.ext_arm + erow : nullptr;
+        if (ext) tr.sigma_amp = tr.sigma_df = 0.0;  // external series replace the internal draws, missing ones are zero
         double* phi = P.scratch + j * P.N;
         // ---- normalisation of the waveform: max |g| over the trial (physics.py:668-669) ----
         double gmax = 0.0;
@@ -109,7 +126,8 @@ __global__ void __launch_bounds__(kAsdThreads) synth_asd_kernel(const AsdParams 
                 double inc = 0.0;
                 if (i < P.N) {
                     const double g = asd_waveform(tr, P, i) * ginv;
-                    const double dfn = tr.sigma_df != 0.0 ? tr.df + tr.sigma_df * static_cast<double>(z[e]) : tr.df;
+                    const double dfn = e_df ? tr.df + e_df[i]
+                                            : (tr.sigma_df != 0.0 ? tr.df + tr.sigma_df * static_cast<double>(z[e]) : tr.df);
                     inc = dfn * g;
                 }
                 run += inc;
@@ -143,13 +161,21 @@ __global__ void __launch_bounds__(kAsdThreads) synth_asd_kernel(const AsdParams 
                 const long long i = i0 + e;
                 if (i >= P.N) break;
                 const double t = static_cast<double>(i) / P.fs;
-                const double path = tr.arm_amp != 0.0 ? tr.arm_amp * sin(tr.arm_w * t + tr.arm_psi) + 0.0 + tr.path0 : tr.path0;
+                double path;
+                if (e_arm)  // physics.py:686-688: modulation + noise + static offset, in this order
+                    path = (tr.arm_amp != 0.0 ? tr.arm_amp * sin(tr.arm_w * t + tr.arm_psi) : 0.0) + e_arm[i] + tr.path0;
+                else
+                    path = tr.arm_amp != 0.0 ? tr.arm_amp * sin(tr.arm_w * t + tr.arm_psi) + 0.0 + tr.path0 : tr.path0;
                 const double tau_dl = path / kLightSpeed;
                 const double pm_meas = asd_interp(phi, P.N, P.fs, scale, t - (tr.tau_m + tau_dl));
                 const double pm_ref = asd_interp(phi, P.N, P.fs, scale, t - tr.tau_r);
-                const double geom = tr.omega0 * ((tr.tau_m + tau_dl) - tr.tau_r);
-                const double phase = geom + (pm_meas - pm_ref);
-                const double a = tr.sigma_amp != 0.0 ? tr.amp + tr.sigma_amp * static_cast<double>(z[e]) : tr.amp;
+                const double lag = (tr.tau_m + tau_dl) - tr.tau_r;
+                const double geom = tr.omega0 * lag;
+                // physics.py:703-705: the carrier term with the noisy optical frequency f0 + n_f(t)
+                const double carrier = e_fn ? (2.0 * kPi * (tr.omega0 / (2.0 * kPi) + e_fn[i])) * lag : geom;
+                const double phase = carrier + (pm_meas - pm_ref);
+                const double a = e_amp ? tr.amp + e_amp[i]
+                                       : (tr.sigma_amp != 0.0 ? tr.amp + tr.sigma_amp * static_cast<double>(z[e]) : tr.amp);
                 P.y[j * P.ld + i] = a * (1.0 + tr.vis * cos(phase));
                 if (P.truth) P.truth[j * P.ld + i] = geom;
             }

@@ -10,7 +10,14 @@ extern "C" {
 
 int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, int64_t N, double f_samp,
                       const double* tables_dev, int64_t ntables, double* y_dev, int64_t ld, double* truth_dev) {
+    return dfk_synth_asd_noise_dev(ctx, trials_dev, ntrials, N, f_samp, tables_dev, ntables, nullptr, 0, y_dev, ld, truth_dev);
+}
+
+int dfk_synth_asd_noise_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, int64_t N, double f_samp,
+                            const double* tables_dev, int64_t ntables, const double* const* noise_dev, int64_t noise_rows,
+                            double* y_dev, int64_t ld, double* truth_dev) {
     DFK_ENTER(ctx);
+    if (noise_rows < 0 || (noise_rows > 0 && !noise_dev)) return fail(DFK_ERR_ARG, "bad external noise series");
     if (ntrials < 0 || N < 0 || ld < N) return fail(DFK_ERR_ARG, "bad geometry: ntrials=%lld N=%lld ld=%lld", (long long)ntrials, (long long)N, (long long)ld);
     if (!(f_samp > 0.0)) return fail(DFK_ERR_ARG, "f_samp must be positive");
     if (ntrials == 0 || N == 0) return DFK_OK;
@@ -31,6 +38,10 @@ int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, i
     P.y = y_dev;
     P.ld = ld;
     P.truth = truth_dev;
+    P.ext_fn = noise_rows ? noise_dev[DFK_NOISE_LASER_FREQUENCY] : nullptr;
+    P.ext_amp = noise_rows ? noise_dev[DFK_NOISE_AMPLITUDE] : nullptr;
+    P.ext_df = noise_rows ? noise_dev[DFK_NOISE_DF] : nullptr;
+    P.ext_arm = noise_rows ? noise_dev[DFK_NOISE_ARMLENGTH] : nullptr;
     const int grid = static_cast<int>(std::min<int64_t>(ntrials, static_cast<int64_t>(ctx->sm_count) * 32));
     dfk::synth_asd_kernel<<<grid, dfk::kAsdThreads, 0, ctx->stream()>>>(P);
     ctx->launches++;

@@ -77,16 +77,15 @@ class DFMIObject:
 
 class SignalGenerator:
     """The reference's physics engine by name (physics.py:362-421): ``generate`` returns the records keyed 'main' and
-    'witness', produced by the device generators (simulation.py).  Pre-computed noise arrays (``external_noise``) are
-    a host-side injection the device generator has no input for: asking for them raises."""
+    'witness', produced by the device generators (simulation.py); ``external_noise`` series replace the internally
+    drawn noise as in the reference (and are ignored in 'snr' mode, physics.py:418)."""
 
     def generate(self, main_config, n_seconds, mode="asd", trial_num=0, witness_config=None, snr_db=None,
                  external_noise=None):
         from .simulation import simulate
         if mode == "asd":
-            if external_noise:
-                raise NotImplementedError("external noise arrays are not taken by the device generator")
-            out = simulate(main_config, n_seconds, mode="asd", trial_num=trial_num, witness=witness_config)
+            out = simulate(main_config, n_seconds, mode="asd", trial_num=trial_num, witness=witness_config,
+                           external_noise=external_noise)
             return {"main": out[0], "witness": out[1]} if witness_config is not None else {"main": out}
         if mode == "snr":
             if snr_db is None:

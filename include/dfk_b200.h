@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DFK_ABI_VERSION 3
+#define DFK_ABI_VERSION 4
 #define DFK_ROW_STRIDE 8
 #define DFK_MAX_HARMONICS 64
 
@@ -296,8 +296,10 @@ int dfk_ingest_binary_file(dfk_ctx* ctx, const char* path, int64_t byte_offset, 
  *   [7] meas_arml / c  [8] phi wavelength / (2 pi)  [9] arml_mod_amp  [10] 2 pi arml_mod_f  [11] arml_mod_psi
  *   [12] amp_n sqrt(fs/2)  [13] df_n sqrt(fs/2)  [14] noise key (the trial number)  [15] number of waveform terms
  *   (0: the waveform is row [16] of the tables)  [17 + 3k ..] harmonic h_k, amplitude a_k, phase p_k of term k < 6:
- *   g(theta) = sum_k a_k cos(h_k theta + p_k), normalised to max |g| = 1 over the trial. */
-#define DFK_ASD_TRIAL_DOUBLES 35
+ *   g(theta) = sum_k a_k cos(h_k theta + p_k), normalised to max |g| = 1 over the trial.
+ *   [35] != 0: the channel is dynamic (the main channel; a witness is static, physics.py:460)
+ *   [36] row of the external noise series this trial reads (dfk_synth_asd_noise_dev), or < 0 for internal noise. */
+#define DFK_ASD_TRIAL_DOUBLES 37
 #define DFK_TRIAL_STATS_DOUBLES 6
 /* The reference simulates every trial of an Experiment on its own (experiments.py:15-88 -> SignalGenerator.generate,
  * mode 'asd'); here all trials of a batch are produced at once, N samples each: y_dev[j * ld + i].  tables_dev:
@@ -306,6 +308,19 @@ int dfk_ingest_binary_file(dfk_ctx* ctx, const char* path, int64_t byte_offset, 
  * modulation-depth noise only; statistically, not bitwise, the reference's MT19937 draws. */
 int dfk_synth_asd_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, int64_t N, double f_samp,
                       const double* tables_dev, int64_t ntables, double* y_dev, int64_t ld, double* truth_dev);
+/* The same with pre-computed noise series, the engine's external_noise input (SignalGenerator.generate, physics.py:
+ * 380-434; _run_simulation_physics :672-710): noise_dev[4] holds device pointers to noise_rows x N series -- laser
+ * frequency [Hz], amplitude, modulation amplitude df [Hz], arm length [m] -- any of which may be NULL (taken as zero).
+ * A trial whose record names a row ([36] >= 0) reads that row of each series INSTEAD of drawing white noise; the
+ * arm-length series only if the trial is dynamic ([35]).  This is how coloured laser-frequency and arm-length noise,
+ * which the reference takes from a third-party generator, enter: main and witness channel of a pair name the same row. */
+#define DFK_NOISE_LASER_FREQUENCY 0
+#define DFK_NOISE_AMPLITUDE 1
+#define DFK_NOISE_DF 2
+#define DFK_NOISE_ARMLENGTH 3
+int dfk_synth_asd_noise_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntrials, int64_t N, double f_samp,
+                            const double* tables_dev, int64_t ntables, const double* const* noise_dev, int64_t noise_rows,
+                            double* y_dev, int64_t ld, double* truth_dev);
 /* Per grid point and result column: nanmean, nanstd, nanmin, nanmax, "worst" (the trial farthest from the mean)
  * and the number of finite trials -- the aggregation at the end of Experiment.run (experiments.py:432-446).
  * values_dev[(p * ntrials + t) * col_stride + c]; out_dev[(p * ncols + c) * 6 + {0..5}].  center_dev (npoints x

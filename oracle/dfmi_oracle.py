@@ -433,21 +433,31 @@ def asd_signal(m_target: float, f_samp: float, f_mod: float, n_seconds: float, t
                amp_n: float = 0.0, df_n: float = 0.0, arml_mod_amp: float = 0.0, arml_mod_f: float = 5.0,
                arml_mod_psi: float = 0.0, phi0: float = 0.0, psi0: float = 0.0, amp: float = 1.0,
                visibility: float = 1.0, wavelength: float = 1.064e-6, ref_arml: float = 0.1,
-               meas_arml: float = 0.3, dynamic: bool = True):
+               meas_arml: float = 0.3, dynamic: bool = True, df: float = None, external_noise: dict = None):
     """'asd'-mode record of the reference's exact physical model (physics.py:423-440, 557-611, 615-722).
 
     Only the white noise sources (``amp_n``, ``df_n``: ``RandomState(1 + 4*trial).normal``, amplitude drawn before
     df, physics.py:581-597) are restated; the coloured ones (``f_n``, ``arml_mod_n``) need ``pyplnoise``, a
-    third-party generator that is absent from the reference checkout and from this image.
+    third-party generator that is absent from the reference checkout and from this image.  ``external_noise``
+    (physics.py:430-434) replaces all internal draws by given series -- keys 'laser_frequency', 'amplitude', 'df',
+    'armlength', missing ones zero -- which is how those two sources can still be exercised.
     The arm-length modulation makes the interferometric phase walk: the record drifting fits are tested on.
     Returns (signal, ground-truth phase).
     """
     n = int(n_seconds * f_samp)
     t = np.arange(n) / f_samp
-    df = laser_df(m_target, ref_arml, meas_arml)
-    rng = np.random.RandomState(seed=1 + trial * 4)  # physics.py:577-580
-    noise_amp = rng.normal(scale=amp_n * np.sqrt(f_samp / 2.0), size=n) if amp_n != 0.0 else 0.0
-    noise_df = rng.normal(scale=df_n * np.sqrt(f_samp / 2.0), size=n) if df_n != 0.0 else 0.0
+    if df is None:
+        df = laser_df(m_target, ref_arml, meas_arml)
+    noise_f = noise_arm = 0.0
+    if external_noise:
+        noise_amp = external_noise.get("amplitude", 0.0)
+        noise_df = external_noise.get("df", 0.0)
+        noise_f = external_noise.get("laser_frequency", 0.0)
+        noise_arm = external_noise.get("armlength", 0.0)
+    else:
+        rng = np.random.RandomState(seed=1 + trial * 4)  # physics.py:577-580
+        noise_amp = rng.normal(scale=amp_n * np.sqrt(f_samp / 2.0), size=n) if amp_n != 0.0 else 0.0
+        noise_df = rng.normal(scale=df_n * np.sqrt(f_samp / 2.0), size=n) if df_n != 0.0 else 0.0
     omega_mod = 2 * np.pi * f_mod
     g = np.cos(omega_mod * t + psi0)  # default waveform_func (physics.py:44)
     peak = np.max(np.abs(g))
@@ -460,12 +470,12 @@ def asd_signal(m_target: float, f_samp: float, f_mod: float, n_seconds: float, t
     if not dynamic:
         path = phi0 * wavelength / (2 * np.pi)
     else:
-        path = (arml_mod_amp * np.sin(2 * np.pi * arml_mod_f * t + arml_mod_psi) + 0.0
+        path = (arml_mod_amp * np.sin(2 * np.pi * arml_mod_f * t + arml_mod_psi) + noise_arm
                 + phi0 * wavelength / (2 * np.pi))
     tau_dl = path / SPEED_OF_LIGHT
     pm_meas = np.interp(t - (tau_m + tau_dl), t, phi_mod)
     pm_ref = np.interp(t - tau_r, t, phi_mod)
-    f0 = (SPEED_OF_LIGHT / wavelength) + 0.0
+    f0 = (SPEED_OF_LIGHT / wavelength) + noise_f
     carrier = (2 * np.pi * f0) * ((tau_m + tau_dl) - tau_r)
     phase = carrier + (pm_meas - pm_ref)
     signal = (amp + noise_amp) * (1 + visibility * np.cos(phase))

@@ -62,6 +62,13 @@ def fit_file_cases(out, tmp):
                                         dtype=float)
 
 
+def external_noise(n):
+    """Deterministic noise series (the tests regenerate them from the same seed)."""
+    rng = np.random.RandomState(11)
+    return {"laser_frequency": np.cumsum(rng.randn(n)) * 2e3, "amplitude": rng.randn(n) * 1e-3,
+            "df": rng.randn(n) * 3e4, "armlength": np.cumsum(rng.randn(n)) * 1e-10}
+
+
 def witness_cases(out):
     dff = core.DeepFitFramework()
     laser = core.LaserConfig(psi=0.3)
@@ -84,6 +91,15 @@ def witness_cases(out):
         raw = dff.raws[label]
         out[f"wit_{key}_data"] = raw.data.values.flatten()
         out[f"wit_{key}_phi_sim"] = np.asarray(raw.phi_sim, dtype=float)
+    # the same pair with pre-computed noise in all four sources (SignalGenerator.generate(external_noise=...)):
+    # random-walk laser-frequency and arm-length noise, white amplitude and df noise
+    chans = core.SignalGenerator().generate(main, 0.02, mode="asd", trial_num=0, witness_config=dff.sims["w_m"],
+                                            external_noise=external_noise(4000))
+    for key in ("main", "witness"):
+        out[f"ext_{key}_data"] = chans[key].data.values.flatten()
+        out[f"ext_{key}_phi_sim"] = np.asarray(chans[key].phi_sim, dtype=float)
+    only_f = {"laser_frequency": external_noise(4000)["laser_frequency"]}
+    out["ext_onlyf_data"] = core.SignalGenerator().generate(main, 0.02, mode="asd", external_noise=only_f)["main"].data.values.flatten()
 
 
 def helper_cases(out):

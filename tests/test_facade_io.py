@@ -277,3 +277,60 @@ def test_experiment_accepts_the_wdfmi_factory_for_gpu_analyses(torch_mod):
     exp.add_analysis("w", "wdfmi_ortho")
     with pytest.raises(NotImplementedError):
         exp.run()
+
+
+# ------------------------------------------------------------------ pre-computed noise series (external_noise)
+def _external_noise(n):
+    rng = np.random.RandomState(11)  # as tests/golden/make_golden_facade_io.py
+    return {"laser_frequency": np.cumsum(rng.randn(n)) * 2e3, "amplitude": rng.randn(n) * 1e-3,
+            "df": rng.randn(n) * 3e4, "armlength": np.cumsum(rng.randn(n)) * 1e-10}
+
+
+def test_oracle_external_noise_matches_reference(golden):
+    """The oracle's 'asd' physics with all four noise sources injected == the reference engine's records."""
+    from oracle import dfmi_oracle as orc
+    g = golden("facade_io")
+    df, wavelength, psi, f_mod = g["wit_laser"]
+    ref_arml, meas_arml, phi, aamp, af, apsi = g["wit_main_ifo"]
+    noise = _external_noise(4000)
+    common = dict(m_target=0.0, f_samp=200e3, f_mod=f_mod, n_seconds=0.02, psi0=psi, wavelength=wavelength, df=df)
+    y, truth = orc.asd_signal(phi0=phi, ref_arml=ref_arml, meas_arml=meas_arml, arml_mod_amp=aamp, arml_mod_f=af,
+                              arml_mod_psi=apsi, external_noise=noise, **common)
+    assert np.max(np.abs(y - g["ext_main_data"])) < 1e-12 and np.array_equal(truth, g["ext_main_phi_sim"])
+    w_ref, w_meas, w_phi = g["wit_configs"][1][:3]
+    yw, tw = orc.asd_signal(phi0=w_phi, ref_arml=w_ref, meas_arml=w_meas, dynamic=False, external_noise=noise, **common)
+    assert np.max(np.abs(yw - g["ext_witness_data"])) < 1e-12 and np.array_equal(tw, g["ext_witness_phi_sim"])
+    yf, _ = orc.asd_signal(phi0=phi, ref_arml=ref_arml, meas_arml=meas_arml, arml_mod_amp=aamp, arml_mod_f=af,
+                           arml_mod_psi=apsi, external_noise={"laser_frequency": noise["laser_frequency"]}, **common)
+    assert np.max(np.abs(yf - g["ext_onlyf_data"])) < 1e-12
+    # the noise matters at the level the gate can see
+    assert np.max(np.abs(g["ext_main_data"] - g["wit_main_data"])) > 1e-3
+
+
+@pytest.mark.gpu
+def test_device_external_noise_matches_reference(torch_mod, golden):
+    from deepfmkit_b200 import physics
+    g = golden("facade_io")
+    dff = _main_and_witness(g)
+    noise = _external_noise(4000)
+    main, wit = dff.sims["main"], dff.sims["w_m"]
+    main.laser.amp_n = 5e-3  # internal noise settings are ignored once series are handed in (physics.py:430-434)
+    chans = physics.SignalGenerator().generate(main, 0.02, mode="asd", trial_num=0, witness_config=wit, external_noise=noise)
+    for key in ("main", "witness"):
+        y = chans[key].data.values.flatten()
+        dev = np.max(np.abs(y - g[f"ext_{key}_data"]))
+        assert dev < 2e-8, (key, dev)
+        truth = chans[key].phi_sim.cpu().numpy()
+        assert np.max(np.abs(truth - g[f"ext_{key}_phi_sim"])) <= 4e-15 * np.max(np.abs(truth)), key
+    # a subset of the sources, CUDA tensors as input
+    only_f = {"laser_frequency": torch_mod.from_numpy(noise["laser_frequency"]).cuda()}
+    y = physics.SignalGenerator().generate(main, 0.02, mode="asd", external_noise=only_f)["main"].data.values.flatten()
+    assert np.max(np.abs(y - g["ext_onlyf_data"])) < 2e-8
+    # coloured-noise settings no longer stop a simulation whose noise is handed in ...
+    main.laser.f_n = 10.0
+    physics.SignalGenerator().generate(main, 0.02, mode="asd", external_noise=noise)
+    # ... and still do when it would have to be generated
+    with pytest.raises(NotImplementedError):
+        physics.SignalGenerator().generate(main, 0.02, mode="asd")
+    with pytest.raises(ValueError):
+        physics.SignalGenerator().generate(main, 0.02, mode="asd", external_noise={"df": 3.0})
