@@ -351,7 +351,7 @@ def event_timed(torch, stream, fn, reps, warm=1):
 
 
 def nls_config(torch, ctx, stream, clocks, name, f_samp, n, ndata, channels, seconds, reps, peak, fp64_peak, m_list=None,
-               note=""):
+               note="", waves=1):
     """One NLS config, device-generated and resident: whole readout, demod and LM times, both rooflines."""
     import numpy as np
     from deepfmkit_b200 import _lib
@@ -410,6 +410,23 @@ def nls_config(torch, ctx, stream, clocks, name, f_samp, n, ndata, channels, sec
            "lm": {"kernel_ms": lm_ms, "share_of_step": lm_ms / ms, "fits_per_sec": nbuf / (lm_ms * 1e-3), "per_fit": per_fit,
                   "roofline": {"bound": "fp64", "achieved": lm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                "frac": lm_tf / fp64_peak if fp64_peak else None, "flop_per_fit": flop_per_fit}}}
+    if waves > 1:
+        # the whole config: `waves` consecutive waves of every channel, each generated on the device where the previous
+        # one lay (t0 advances, so the record is the continuous one) and fitted -- generation inside the timed region
+        def all_waves():
+            for w in range(waves):
+                ctx.synth_snr_slab_dev(x.data_ptr(), T, channels, T, w * T, f_samp, F_MOD, 6.0, dphi=2 * np.pi / channels, seed=5)
+                whole()
+
+        with clocks:
+            ms_all = event_timed(torch, stream, all_waves, 2, warm=1)
+        r = rows[:: max(1, nbuf // 4096)].cpu().numpy()
+        assert abs(float(np.mean(r[:, 1])) - truth_m) < 0.05 and np.mean(r[:, 6] == 0) > 0.9, f"{name}: last wave is wrong"
+        out["whole_config"] = {"waves": waves, "buffers": nbuf * waves, "samples": nbuf * Rc * waves,
+                               "record_bytes": nbuf * Rc * 8 * waves, "ms_incl_generator": ms_all,
+                               "buffers_per_sec": nbuf * waves / (ms_all * 1e-3),
+                               "note": "each wave device-generated in place of the previous one, then fitted; every "
+                                       "wave fits its own buffer 0 cold"}
     del x, rows, init_dev
     torch.cuda.empty_cache()
     return out
@@ -484,7 +501,7 @@ def other_configs(torch, ctx, stream, clocks, peak, fp64_peak, with_cpu):
                              note="cfg1 README quickstart: 1 channel x 10 s at 200 kHz = 500 buffers of 4000 (launch bound)")
     out["cfg3"] = nls_config(torch, ctx, stream, clocks, "cfg3", 200e3, 20, 10, 256, 100.0, 20, peak, fp64_peak,
                              note="cfg3 resident wave: 256 channels x 100 s of the 1000 s config = 1.28e6 buffers, 41 GB "
-                                  "(the full config is ten such waves per GPU, or 1.25 per GPU on 8)")
+                                  "(the full config is ten such waves per GPU, or 1.25 per GPU on 8: whole_config)", waves=10)
     out["cfg4"] = ekf_config(torch, ctx, stream, clocks, 4096, 100.0, 1.0, peak, fp64_peak)
     ms = list(range(2, 21))
     out["cfg5"] = nls_config(torch, ctx, stream, clocks, "cfg5", 200e3, 1, 15, 1_000_000 * len(ms), 1e-3, 10, peak,
