@@ -56,10 +56,11 @@ DFK_D double synth_clean(const SynthParams& p, double phi, long long t) {
 }
 
 // The four samples t = 4q .. 4q+3 of channel c.  FIRST_PERIOD: the caller guarantees 4q + 3 < P (a record of one
-// period), which spares the 64-bit remainder that finds the quad's place in the tabulated period.
+// period), which spares the 64-bit remainder that finds the quad's place in the tabulated period; so does a caller
+// that tracks the place itself and hands it over as jm0 = 4q mod P (>= 0).
 template <bool FIRST_PERIOD = false>
 DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
-                             long long q, double y[4]) {
+                             long long q, double y[4], int jm0 = -1) {
     const unsigned long long key = p.seed + static_cast<unsigned long long>(c);
     uint32_t r[4];
     philox4x32_10(static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), 0x5eedu, 0u, static_cast<uint32_t>(key),
@@ -70,7 +71,7 @@ DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clea
         box_muller(r[2 * h], r[2 * h + 1], z[2 * h], z[2 * h + 1]);
     }
     const long long t4 = q << 2;
-    int jm = table ? (FIRST_PERIOD ? static_cast<int>(t4) : static_cast<int>(t4 % p.P)) : 0;
+    int jm = table ? (FIRST_PERIOD ? static_cast<int>(t4) : (jm0 >= 0 ? jm0 : static_cast<int>(t4 % p.P))) : 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         double clean;
@@ -86,9 +87,9 @@ DFK_D void synth_quad_values(const SynthParams& p, int table, const double* clea
 }
 
 DFK_D void synth_quad(const SynthParams& p, int table, const double* clean_tab, double phi, double sigma, long long c,
-                      long long q) {
+                      long long q, int jm0 = -1) {
     double y[4];
-    synth_quad_values(p, table, clean_tab, phi, sigma, c, q, y);
+    synth_quad_values(p, table, clean_tab, phi, sigma, c, q, y, jm0);
     const long long t4 = q << 2;
     double* dst = p.x + c * p.ld_c - p.t0 + t4;  // indexed by absolute t
     if (t4 >= p.t0 && t4 + 4 <= p.t0 + p.T && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
@@ -119,22 +120,51 @@ __global__ void __launch_bounds__(kSynthThreads) synth_snr_kernel(const SynthPar
         __syncthreads();
         return sigma_sh;
     };
+    // The quads of one channel, strided over the grid's x dimension.  The place in the tabulated period advances by a
+    // fixed step per trip, so the 64-bit remainder is taken once per thread and channel, not once per quad (software
+    // 64-bit division is ~60 instructions next to the ~150 of a quad: the generator is bound by integer issue).
+    auto channel = [&](long long c, double phi, double sigma) {
+        long long q = q_first + first;
+        int jm = table ? static_cast<int>((q << 2) % p.P) : -1;
+        const int step = table ? static_cast<int>((stride << 2) % p.P) : 0;
+        const int P = static_cast<int>(p.P);
+        for (; q < q_end; q += stride) {
+            synth_quad(p, table, clean_tab, phi, sigma, c, q, jm);
+            if (table) {
+                jm += step;
+                if (jm >= P) jm -= P;
+            }
+        }
+    };
     if (p.dphi == 0.0 || c_hi - c_lo == 1) {
-        // one phase for the whole block: its (channel, quad) pairs are one flat index space, so that short
-        // records (one period per channel in the Monte-Carlo shape) still fill every thread
         const double phi = p.phi0 + static_cast<double>(c_lo) * p.dphi;
         const double sigma = prepare(phi);
+        if (c_hi - c_lo == 1) {
+            channel(c_lo, phi, sigma);
+            return;
+        }
+        // one phase for several short records: their (channel, quad) pairs are one flat index space, so that records
+        // of one period (the Monte-Carlo shape) still fill every thread; 32-bit index arithmetic whenever it fits
         const long long total = (c_hi - c_lo) * nq;
-        for (long long i = first; i < total; i += stride) {
-            const long long dc = i / nq;
-            synth_quad(p, table, clean_tab, phi, sigma, c_lo + dc, q_first + (i - dc * nq));
+        if (total < 0x7fffffffll && q_end < 0x1fffffffll) {
+            const unsigned nq32 = static_cast<unsigned>(nq), P32 = static_cast<unsigned>(table ? p.P : 1);
+            for (unsigned i = static_cast<unsigned>(first); i < static_cast<unsigned>(total); i += static_cast<unsigned>(stride)) {
+                const unsigned dc = i / nq32;
+                const unsigned q = static_cast<unsigned>(q_first) + (i - dc * nq32);
+                synth_quad(p, table, clean_tab, phi, sigma, c_lo + dc, q, table ? static_cast<int>((q << 2) % P32) : -1);
+            }
+        } else {
+            for (long long i = first; i < total; i += stride) {
+                const long long dc = i / nq;
+                synth_quad(p, table, clean_tab, phi, sigma, c_lo + dc, q_first + (i - dc * nq));
+            }
         }
         return;
     }
     for (long long c = c_lo; c < c_hi; ++c) {
         const double phi = p.phi0 + static_cast<double>(c) * p.dphi;
         const double sigma = prepare(phi);
-        for (long long i = first; i < nq; i += stride) synth_quad(p, table, clean_tab, phi, sigma, c, q_first + i);
+        channel(c, phi, sigma);
     }
 }
 
