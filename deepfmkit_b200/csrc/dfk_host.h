@@ -4,7 +4,9 @@
 #include "../../include/dfk_b200.h"
 
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
 #include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <cstdarg>
@@ -268,6 +270,7 @@ inline HostCopyTuning& host_copy_tuning() {
 }
 
 // memcpy with streaming stores; dst 32-byte aligned
+#if defined(__x86_64__)
 __attribute__((target("avx2"))) inline void stream_copy(char* dst, const char* src, size_t bytes) {
     size_t i = 0;
     for (; i + 128 <= bytes; i += 128) {
@@ -283,13 +286,18 @@ __attribute__((target("avx2"))) inline void stream_copy(char* dst, const char* s
     _mm_sfence();
     if (i < bytes) std::memcpy(dst + i, src + i, bytes - i);
 }
+inline bool have_stream_copy() { return __builtin_cpu_supports("avx2"); }
+#else
+inline void stream_copy(char* dst, const char* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+inline bool have_stream_copy() { return false; }
+#endif
 
 inline void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     CopyPool& pool = CopyPool::instance();
     const HostCopyTuning& tune = host_copy_tuning();
     const int nt = static_cast<int>(
         std::min<size_t>(static_cast<size_t>(std::min(pool.size(), std::max(1, tune.threads))), bytes / (1u << 20) + 1));
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_avx2 = have_stream_copy();
     const bool streaming = tune.nt && have_avx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
     if (nt <= 1) {
         std::memcpy(dst, src, bytes);
