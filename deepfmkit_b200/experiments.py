@@ -122,9 +122,10 @@ class Experiment:
             self.results = pickle.load(f)
 
     # ---- execution --------------------------------------------------------------------------------------------
-    def _jobs(self):
+    def _jobs(self, first_trial_only=False):
         """The reference's job list (experiments.py:318-372): grid points in itertools.product order, n_trials jobs
-        each, trial numbers counting up across the whole experiment, stochastic generators called per job in order."""
+        each, trial numbers counting up across the whole experiment, stochastic generators called per job in order.
+        first_trial_only: trial 0 of every point (its counter still counts all trials)."""
         axis_names = list(self.axes.keys())
         combos = list(itertools.product(*[range(len(ax)) for ax in self.axes.values()]))
         counter = 0
@@ -132,7 +133,7 @@ class Experiment:
             point_params = copy.deepcopy(self.static_params)
             for i, name in enumerate(axis_names):
                 point_params[name] = self.axes[name][point[i]]
-            for j in range(self.n_trials):
+            for j in range(1 if first_trial_only else self.n_trials):
                 tp = copy.deepcopy(point_params) if self.stochastic_vars else dict(point_params)
                 tp["_exp_point_idx"] = point
                 tp["_exp_trial_idx"] = j
@@ -141,7 +142,7 @@ class Experiment:
                     tp[var_name] = var_info["generator"](tp[dep]) if dep else var_info["generator"]()
                 yield point, j, counter, {k: v for k, v in tp.items()
                                           if k in self._expected_params_keys or k.startswith("_exp_")}
-                counter += 1
+                counter += self.n_trials if first_trial_only else 1
 
     def run(self, n_cores: Optional[int] = None, filename: Optional[str] = None, device: int = 0,
             max_resident_bytes: int = 8 << 30) -> Dict[str, Any]:
@@ -166,15 +167,9 @@ class Experiment:
         tables = None
         f_mod = None
         n_samples = None
-        cached = {}
-        for point, j, counter, params in self._jobs():
-            key = point if not self.stochastic_vars else None
-            hit = cached.get(key) if key is not None else None
-            if hit is not None:  # same physics as the point's first trial: only the noise key differs
-                records[counter] = hit[0]
-                records[counter, 14] = float(counter)
-                df_of[counter] = hit[1]
-                continue
+
+        def pack(params, counter):
+            nonlocal tables, f_mod, n_samples
             cfg = self.config_factory(params)
             # a 'witness_ifo_config' (the W-DFMI factory) is simulated by the reference beside the main channel and read by
             # its W-DFMI fitters only; the analyses run here ('nls', 'ekf': checked above) never look at it
@@ -187,10 +182,20 @@ class Experiment:
                 tables = WaveformTables(n_samples, f_samp)
             elif laser.f_mod != f_mod:
                 raise NotImplementedError("all trials of an experiment must share the modulation frequency")
-            records[counter] = pack_asd_trial(laser, ifo, f_samp, counter, tables, dynamic=True)
-            df_of[counter] = laser.df
-            if key is not None:
-                cached[key] = (records[counter].copy(), laser.df)
+            return pack_asd_trial(laser, ifo, f_samp, counter, tables, dynamic=True), laser.df
+
+        if not self.stochastic_vars:
+            # every trial of a grid point has the point's physics; only the noise key (the trial number, counted across
+            # the whole experiment as in experiments.py:318-372) differs: one factory call per point, the rest is array work
+            for pi, (point, j, counter, params) in enumerate(self._jobs(first_trial_only=True)):
+                rec, df = pack(params, counter)
+                lo = pi * ntr
+                records[lo:lo + ntr] = rec
+                records[lo:lo + ntr, 14] = np.arange(lo, lo + ntr, dtype=np.float64)
+                df_of[lo:lo + ntr] = df
+        else:
+            for point, j, counter, params in self._jobs():
+                records[counter], df_of[counter] = pack(params, counter)
 
         # ---- 2. simulate and fit in waves ----------------------------------------------------------------------------
         dev = torch.device("cuda", device)
