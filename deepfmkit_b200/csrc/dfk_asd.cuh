@@ -187,115 +187,221 @@ __global__ void __launch_bounds__(kAsdThreads) synth_asd_kernel(const AsdParams 
 // ---------------------------------------------------------------------------------------------------------------
 // Reduction of a batch of trial results to the statistics Experiment.run reports per grid point
 // (experiments.py:432-446): nanmean, nanstd (population), nanmin, nanmax and the "worst" trial, the value farthest
-// from the mean (or from center[point][col] when given).  values[point][trial][col] with a column stride; one CTA per
-// (point, column).
+// from the mean (or from center[point][col] when given).  values[point][trial][col] with a column stride.
+// A grid point's trials are cut into slices, one CTA per (slice, point); a thread takes whole rows, so that the table
+// is read by coalesced row loads once per pass whatever the number of columns (a CTA per (point, column) striding over
+// the rows ran at 0.5 TB/s on the 19 x 1e6 table of the Monte-Carlo sweep).  Pass 1: sum, count, min, max per slice.
+// Pass 2: every CTA forms the point's mean from the slice partials, then its slice's centred sum of squares and
+// farthest trial.  Finish: one thread per (point, column) combines the slices in slice order (deterministic).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStatThreads = 256;
+constexpr int kStatMaxCols = 8;
+constexpr int kStatMaxSlices = 64;
 
 struct TrialStats {
     double mean, std, min, max, worst, count;
 };
+struct StatPart1 {
+    double sum, cnt, mn, mx;
+};
+struct StatPart2 {
+    double q, far;
+    long long far_t;
+    long long pad;
+};
 
-__global__ void __launch_bounds__(kStatThreads) trial_stats_kernel(const double* __restrict__ values, long long npoints,
-                                                                  long long ntrials, int ncols, long long col_stride,
-                                                                  const double* __restrict__ center,
-                                                                  TrialStats* __restrict__ out) {
-    __shared__ double sh[4][kStatThreads / 32];
-    __shared__ double mean_sh;
+// CTA blockIdx.x = point * nslices + slice
+DFK_D void stat_slice(long long ntrials, int nslices, long long& point, int& slice, long long& lo, long long& hi) {
+    point = blockIdx.x / nslices;
+    slice = static_cast<int>(blockIdx.x - point * nslices);
+    const long long per = (ntrials + nslices - 1) / nslices;
+    lo = slice * per;
+    hi = lo + per < ntrials ? lo + per : ntrials;
+}
+
+__global__ void __launch_bounds__(kStatThreads) trial_stats_pass1(const double* __restrict__ values, long long ntrials,
+                                                                  int ncols, long long col_stride, int nslices,
+                                                                  StatPart1* __restrict__ part) {
+    __shared__ double sh[kStatThreads / 32][kStatMaxCols][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long point = blockIdx.x / ncols;
-    const int col = static_cast<int>(blockIdx.x % ncols);
-    const double* v = values + point * ntrials * col_stride + col;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    double s = 0.0, cnt = 0.0, mn = __longlong_as_double(0x7ff0000000000000ll), mx = -mn;
-    for (long long t = threadIdx.x; t < ntrials; t += kStatThreads) {
-        const double x = v[t * col_stride];
-        if (x == x) {
-            s += x;
-            cnt += 1.0;
-            mn = fmin(mn, x);
-            mx = fmax(mx, x);
-        }
-    }
+    long long point, lo, hi;
+    int slice;
+    stat_slice(ntrials, nslices, point, slice, lo, hi);
+    const double* v = values + point * ntrials * col_stride;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double s[kStatMaxCols], n[kStatMaxCols], mn[kStatMaxCols], mx[kStatMaxCols];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int c = 0; c < kStatMaxCols; ++c) {
+        s[c] = n[c] = 0.0;
+        mn[c] = inf;
+        mx[c] = -inf;
     }
-    if (lane == 0) {
-        sh[0][warp] = s;
-        sh[1][warp] = cnt;
-        sh[2][warp] = mn;
-        sh[3][warp] = mx;
-    }
-    __syncthreads();
-    s = cnt = 0.0;
-    for (int w = 0; w < kStatThreads / 32; ++w) {
-        s += sh[0][w];
-        cnt += sh[1][w];
-        mn = fmin(mn, sh[2][w]);
-        mx = fmax(mx, sh[3][w]);
-    }
-    const double mean = cnt > 0.0 ? s / cnt : nan;
-    if (threadIdx.x == 0) mean_sh = mean;
-    __syncthreads();
-    // second pass: centred sum of squares, and the trial farthest from the mean -- or from a given centre, e.g. the
-    // true value -- (first one on ties, as argmax)
-    const double ref = center ? center[blockIdx.x] : mean_sh;
-    double q = 0.0, far = -1.0;
-    long long far_t = 0x7fffffffffffffffll;
-    for (long long t = threadIdx.x; t < ntrials; t += kStatThreads) {
-        const double x = v[t * col_stride];
-        if (x == x) {
-            const double d = x - mean_sh;
-            q = fma(d, d, q);
-            const double ad = fabs(x - ref);
-            if (ad > far) {
-                far = ad;
-                far_t = t;
+    for (long long t = lo + threadIdx.x; t < hi; t += kStatThreads) {
+        const double* row = v + t * col_stride;
+#pragma unroll
+        for (int c = 0; c < kStatMaxCols; ++c) {
+            if (c < ncols) {
+                const double x = row[c];
+                if (x == x) {
+                    s[c] += x;
+                    n[c] += 1.0;
+                    mn[c] = fmin(mn[c], x);
+                    mx[c] = fmax(mx[c], x);
+                }
             }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-        const double of = __shfl_xor_sync(0xffffffffu, far, o);
-        const long long ot = __shfl_xor_sync(0xffffffffu, far_t, o);
-        if (of > far || (of == far && ot < far_t)) {
-            far = of;
-            far_t = ot;
+    for (int c = 0; c < kStatMaxCols; ++c) {
+        if (c < ncols) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+                n[c] += __shfl_xor_sync(0xffffffffu, n[c], o);
+                mn[c] = fmin(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+                mx[c] = fmax(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            }
+            if (lane == 0) {
+                sh[warp][c][0] = s[c];
+                sh[warp][c][1] = n[c];
+                sh[warp][c][2] = mn[c];
+                sh[warp][c][3] = mx[c];
+            }
         }
     }
-    __shared__ long long far_sh[kStatThreads / 32];
     __syncthreads();
-    if (lane == 0) {
-        sh[0][warp] = q;
-        sh[1][warp] = far;
-        far_sh[warp] = far_t;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        q = 0.0;
-        far = -1.0;
-        far_t = 0x7fffffffffffffffll;
+    if (threadIdx.x < ncols) {
+        const int c = threadIdx.x;
+        StatPart1 r = {0.0, 0.0, inf, -inf};
         for (int w = 0; w < kStatThreads / 32; ++w) {
-            q += sh[0][w];
-            if (sh[1][w] > far || (sh[1][w] == far && far_sh[w] < far_t)) {
-                far = sh[1][w];
-                far_t = far_sh[w];
+            r.sum += sh[w][c][0];
+            r.cnt += sh[w][c][1];
+            r.mn = fmin(r.mn, sh[w][c][2]);
+            r.mx = fmax(r.mx, sh[w][c][3]);
+        }
+        part[(point * nslices + slice) * ncols + c] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kStatThreads) trial_stats_pass2(const double* __restrict__ values, long long ntrials,
+                                                                  int ncols, long long col_stride, int nslices,
+                                                                  const double* __restrict__ center,
+                                                                  const StatPart1* __restrict__ part1,
+                                                                  StatPart2* __restrict__ part2) {
+    __shared__ double mean_sh[kStatMaxCols], ref_sh[kStatMaxCols];
+    __shared__ double shq[kStatThreads / 32][kStatMaxCols], shf[kStatThreads / 32][kStatMaxCols];
+    __shared__ long long sht[kStatThreads / 32][kStatMaxCols];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long point, lo, hi;
+    int slice;
+    stat_slice(ntrials, nslices, point, slice, lo, hi);
+    const double* v = values + point * ntrials * col_stride;
+    if (threadIdx.x < ncols) {
+        const int c = threadIdx.x;
+        double s = 0.0, n = 0.0;
+        for (int k = 0; k < nslices; ++k) {
+            s += part1[(point * nslices + k) * ncols + c].sum;
+            n += part1[(point * nslices + k) * ncols + c].cnt;
+        }
+        const double mean = n > 0.0 ? s / n : __longlong_as_double(0x7ff8000000000000ll);
+        mean_sh[c] = mean;
+        ref_sh[c] = center ? center[point * ncols + c] : mean;
+    }
+    __syncthreads();
+    double mean[kStatMaxCols], ref[kStatMaxCols], q[kStatMaxCols], far[kStatMaxCols];
+    long long far_t[kStatMaxCols];
+#pragma unroll
+    for (int c = 0; c < kStatMaxCols; ++c) {
+        mean[c] = c < ncols ? mean_sh[c] : 0.0;
+        ref[c] = c < ncols ? ref_sh[c] : 0.0;
+        q[c] = 0.0;
+        far[c] = -1.0;
+        far_t[c] = 0x7fffffffffffffffll;
+    }
+    for (long long t = lo + threadIdx.x; t < hi; t += kStatThreads) {
+        const double* row = v + t * col_stride;
+#pragma unroll
+        for (int c = 0; c < kStatMaxCols; ++c) {
+            if (c < ncols) {
+                const double x = row[c];
+                if (x == x) {
+                    const double d = x - mean[c];
+                    q[c] = fma(d, d, q[c]);
+                    const double ad = fabs(x - ref[c]);
+                    if (ad > far[c]) {  // (a thread's trials ascend: the first of equals stays)
+                        far[c] = ad;
+                        far_t[c] = t;
+                    }
+                }
             }
         }
-        TrialStats r;
-        r.mean = mean;
-        r.std = cnt > 0.0 ? sqrt(q / cnt) : nan;
-        r.min = cnt > 0.0 ? mn : nan;
-        r.max = cnt > 0.0 ? mx : nan;
-        r.worst = cnt > 0.0 ? v[far_t * col_stride] : nan;
-        r.count = cnt;
-        out[blockIdx.x] = r;
     }
+#pragma unroll
+    for (int c = 0; c < kStatMaxCols; ++c) {
+        if (c < ncols) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                q[c] += __shfl_xor_sync(0xffffffffu, q[c], o);
+                const double of = __shfl_xor_sync(0xffffffffu, far[c], o);
+                const long long ot = __shfl_xor_sync(0xffffffffu, far_t[c], o);
+                if (of > far[c] || (of == far[c] && ot < far_t[c])) {
+                    far[c] = of;
+                    far_t[c] = ot;
+                }
+            }
+            if (lane == 0) {
+                shq[warp][c] = q[c];
+                shf[warp][c] = far[c];
+                sht[warp][c] = far_t[c];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ncols) {
+        const int c = threadIdx.x;
+        StatPart2 r = {0.0, -1.0, 0x7fffffffffffffffll, 0};
+        for (int w = 0; w < kStatThreads / 32; ++w) {
+            r.q += shq[w][c];
+            if (shf[w][c] > r.far || (shf[w][c] == r.far && sht[w][c] < r.far_t)) {
+                r.far = shf[w][c];
+                r.far_t = sht[w][c];
+            }
+        }
+        part2[(point * nslices + slice) * ncols + c] = r;
+    }
+}
+
+__global__ void trial_stats_finish(const double* __restrict__ values, long long npoints, long long ntrials, int ncols,
+                                   long long col_stride, int nslices, const StatPart1* __restrict__ part1,
+                                   const StatPart2* __restrict__ part2, TrialStats* __restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= npoints * ncols) return;
+    const long long point = i / ncols;
+    const int c = static_cast<int>(i - point * ncols);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll), inf = __longlong_as_double(0x7ff0000000000000ll);
+    double s = 0.0, cnt = 0.0, mn = inf, mx = -inf, q = 0.0, far = -1.0;
+    long long far_t = 0x7fffffffffffffffll;
+    for (int k = 0; k < nslices; ++k) {
+        const StatPart1 a = part1[(point * nslices + k) * ncols + c];
+        const StatPart2 b = part2[(point * nslices + k) * ncols + c];
+        s += a.sum;
+        cnt += a.cnt;
+        mn = fmin(mn, a.mn);
+        mx = fmax(mx, a.mx);
+        q += b.q;
+        if (b.far > far || (b.far == far && b.far_t < far_t)) {
+            far = b.far;
+            far_t = b.far_t;
+        }
+    }
+    TrialStats r;
+    r.mean = cnt > 0.0 ? s / cnt : nan;
+    r.std = cnt > 0.0 ? sqrt(q / cnt) : nan;
+    r.min = cnt > 0.0 ? mn : nan;
+    r.max = cnt > 0.0 ? mx : nan;
+    r.worst = cnt > 0.0 ? values[(point * ntrials + far_t) * col_stride + c] : nan;
+    r.count = cnt;
+    out[i] = r;
 }
 
 }  // namespace dfk

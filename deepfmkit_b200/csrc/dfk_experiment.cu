@@ -2,6 +2,7 @@
 // generator of the reference's physics engine, batched over trials, and the per-grid-point reduction of trial results.
 #include "dfk_host.h"
 
+#include <algorithm>
 #include <cmath>
 
 #include "dfk_asd.cuh"
@@ -57,11 +58,29 @@ int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints,
                     (long long)ntrials, ncols, (long long)col_stride);
     if (npoints == 0) return DFK_OK;
     if (!values_dev || !out_dev) return fail(DFK_ERR_ARG, "null pointer");
-    if (npoints * ncols > 0x7fffffffll) return fail(DFK_ERR_ARG, "too many grid points for one launch");
+    if (ncols > dfk::kStatMaxCols) return fail(DFK_ERR_ARG, "at most %d result columns", dfk::kStatMaxCols);
     static_assert(sizeof(dfk::TrialStats) == DFK_TRIAL_STATS_DOUBLES * sizeof(double), "ABI: statistics record size");
-    dfk::trial_stats_kernel<<<static_cast<unsigned>(npoints * ncols), dfk::kStatThreads, 0, ctx->stream()>>>(
-        values_dev, npoints, ntrials, ncols, col_stride, center_dev, reinterpret_cast<dfk::TrialStats*>(out_dev));
-    ctx->launches++;
+    // slices per grid point: enough CTAs to fill the GPU a few times over, at least a CTA's worth of trials each
+    int64_t nslices = (static_cast<int64_t>(ctx->sm_count) * 4 + npoints - 1) / npoints;
+    nslices = std::max<int64_t>(1, std::min<int64_t>({nslices, static_cast<int64_t>(dfk::kStatMaxSlices),
+                                                      (ntrials + dfk::kStatThreads - 1) / dfk::kStatThreads}));
+    const size_t nparts = static_cast<size_t>(npoints) * nslices * ncols;
+    int rc = ensure(ctx, ctx->stats_part, nparts * (sizeof(dfk::StatPart1) + sizeof(dfk::StatPart2)));
+    if (rc) return rc;
+    auto* part1 = static_cast<dfk::StatPart1*>(ctx->stats_part.ptr);
+    auto* part2 = reinterpret_cast<dfk::StatPart2*>(part1 + nparts);
+    if (npoints * nslices > 0x7fffffffll) return fail(DFK_ERR_ARG, "too many grid points for one launch");
+    const unsigned grid = static_cast<unsigned>(npoints * nslices);
+    cudaStream_t st = ctx->stream();
+    dfk::trial_stats_pass1<<<grid, dfk::kStatThreads, 0, st>>>(values_dev, ntrials, ncols, col_stride,
+                                                               static_cast<int>(nslices), part1);
+    dfk::trial_stats_pass2<<<grid, dfk::kStatThreads, 0, st>>>(values_dev, ntrials, ncols, col_stride,
+                                                               static_cast<int>(nslices), center_dev, part1, part2);
+    const int64_t nout = npoints * ncols;
+    dfk::trial_stats_finish<<<static_cast<unsigned>((nout + 127) / 128), 128, 0, st>>>(
+        values_dev, npoints, ntrials, ncols, col_stride, static_cast<int>(nslices), part1, part2,
+        reinterpret_cast<dfk::TrialStats*>(out_dev));
+    ctx->launches += 3;
     DFK_CUDA(cudaGetLastError());
     return DFK_OK;
 }

@@ -324,7 +324,8 @@ int dfk_synth_asd_noise_dev(dfk_ctx* ctx, const double* trials_dev, int64_t ntri
 /* Per grid point and result column: nanmean, nanstd, nanmin, nanmax, "worst" (the trial farthest from the mean)
  * and the number of finite trials -- the aggregation at the end of Experiment.run (experiments.py:432-446).
  * values_dev[(p * ntrials + t) * col_stride + c]; out_dev[(p * ncols + c) * 6 + {0..5}].  center_dev (npoints x
- * ncols, may be NULL): measure "worst" from these values -- e.g. the true parameters -- instead of the mean. */
+ * ncols, may be NULL): measure "worst" from these values -- e.g. the true parameters -- instead of the mean.
+ * ncols <= 8. */
 int dfk_trial_stats_dev(dfk_ctx* ctx, const double* values_dev, int64_t npoints, int64_t ntrials, int32_t ncols,
                         int64_t col_stride, const double* center_dev, double* out_dev);
 
