@@ -252,6 +252,56 @@ int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int
 
 // nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
 // leave_room: keep enough shared memory free on each SM for a block of the seed fits that run beside this launch
+// Records that do not fold (dfk_demod.cuh, demod_direct_kernel): a warp per buffer, 8 or 16 harmonics per pass, the
+// step table sized to the buffer when it fits beside a second CTA, else to what one CTA may hold.
+template <int KB, bool MULTI, int THREADS>
+int launch_direct_tt(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, int per_sm, cudaStream_t st) {
+    auto kernel = dfk::demod_direct_kernel<KB, MULTI, THREADS>;
+    DFK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t warps_per_cta = THREADS / 32;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((q.nbuf + warps_per_cta - 1) / warps_per_cta,
+                                                                            static_cast<int64_t>(ctx->sm_count) * per_sm)));
+    kernel<<<grid, THREADS, smem, st>>>(q);
+    return DFK_OK;
+}
+
+template <int KB, bool MULTI>
+int launch_direct_t(dfk_ctx* ctx, const dfk::DirectParams& p, int steps, cudaStream_t st) {
+    dfk::DirectParams q = p;
+    q.steps = steps;
+    const size_t smem = (static_cast<size_t>(steps) * KB + static_cast<size_t>(KB) * 32) * sizeof(double2);
+    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, static_cast<size_t>(ctx->smem_per_sm) / (smem + 1024))));
+    // one CTA per SM (a long table): 512 threads, which the 128 registers of the narrower builds allow
+    if (per_sm == 1 && KB <= 12 && !MULTI && dev_int("DFK_DIRECT_THREADS", 512) == 512)
+        return launch_direct_tt<KB, MULTI, 512>(ctx, q, smem, per_sm, st);
+    return launch_direct_tt<KB, MULTI, dfk::kDirectThreads>(ctx, q, smem, per_sm, st);
+}
+
+int launch_direct(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int N, double w0,
+                  double* qi, double* dc, cudaStream_t st) {
+    dfk::DirectParams p = {x, nbuf, bpc, ld_c, R, N, w0, qi, dc, 0};
+    const int64_t need = (R + 31) / 32;  // steps that cover a buffer
+    const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 2048;
+    // harmonics per pass: the narrow builds run twice as fast per pass as the 16-wide one (registers: one CTA of eight
+    // warps per SM), so beyond 16 harmonics several passes of 10 or 12 beat fewer of 16
+    int kb = N <= 8 ? 8 : (N <= 10 ? 10 : (N <= 12 ? 12 : 16));
+    if (N > 16) kb = (N + 11) / 12 < (N + 9) / 10 ? 12 : 10;
+    const int64_t fit1 = static_cast<int64_t>(budget / sizeof(double2) / kb) - 32;
+    if (need <= fit1) {  // the whole buffer in one chunk
+        const int steps = static_cast<int>(need);
+        switch (kb) {
+            case 8: return launch_direct_t<8, false>(ctx, p, steps, st);
+            case 10: return launch_direct_t<10, false>(ctx, p, steps, st);
+            case 12: return launch_direct_t<12, false>(ctx, p, steps, st);
+            default: return launch_direct_t<16, false>(ctx, p, steps, st);
+        }
+    }
+    // long buffers: chunks of what a CTA's table holds, eight harmonics per pass (the chunk sums need a second set of
+    // accumulators)
+    const int64_t fit8 = static_cast<int64_t>(budget / sizeof(double2) / 8) - 32;
+    return launch_direct_t<8, true>(ctx, p, static_cast<int>(std::min<int64_t>(need, fit8)), st);
+}
+
 int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,
                  double* qi, double* dc, cudaStream_t st, bool leave_room = false) {
     if (nbuf == 0) return DFK_OK;
@@ -342,8 +392,8 @@ int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64
         }
         if (rc) return rc;
     } else {
-        const int grid = static_cast<int>(std::min<int64_t>(nbuf, static_cast<int64_t>(ctx->sm_count) * 8));
-        dfk::demod_direct_kernel<<<grid, dfk::kDirectThreads, 0, st>>>(x, nbuf, bpc, ld_c, R, N, w0, qi, dc);
+        const int rc_direct = launch_direct(ctx, x, nbuf, bpc, ld_c, R, N, w0, qi, dc, st);
+        if (rc_direct) return rc_direct;
     }
     ctx->launches++;
     DFK_CUDA(cudaGetLastError());

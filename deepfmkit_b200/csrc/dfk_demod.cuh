@@ -1260,73 +1260,137 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) demod_period_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Lock-in for records that cannot fold (the modulation period is not a small rational number of samples, or the
+// buffer is not whole fold lengths): every sample meets every harmonic, cos/sin of fl(w_k t) as the reference forms
+// them (fit.py:55-64).  Lane l of a warp takes the samples t = c0 + l + 32 j of a buffer, so that
+//     w_k t = w_k (c0 + l) + w_k 32 j,
+// the second term being the same for every lane and every buffer: its cos/sin for j < steps live in a shared-memory
+// table built once per launch (read as broadcasts), and a sample costs its load plus two FMAs per harmonic.  The
+// lane's sums are rotated by w_k (c0 + l) at the end of the chunk -- from a second small table for the first chunk,
+// which is the whole buffer unless it is longer than 32 * steps samples -- then reduced over the warp.
+// KB harmonics per pass over the record (N > KB re-reads it); MULTI: buffers of several chunks.
+// Rotating term by term instead (the first version of this kernel: one complex rotation per sample and harmonic, two
+// sincos per 64 samples to stop its drift) spent 7 fp64 operations where this one spends 2: 0.34 TB/s.
+// ---------------------------------------------------------------------------------------------------
 constexpr int kDirectThreads = 256;
-constexpr int kDirectKB = 8;
-constexpr int kDirectResync = 64;
 
-__global__ void __launch_bounds__(kDirectThreads) demod_direct_kernel(const double* __restrict__ x, long long nbuf,
-                                                                      long long bpc, long long ld_c, long long R, int N,
-                                                                      double w0, double* __restrict__ qi,
-                                                                      double* __restrict__ dc) {
-    __shared__ double red[kDirectThreads / 32][2 * kDirectKB + 1];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (long long b = blockIdx.x; b < nbuf; b += gridDim.x) {
-        const double* buf = x + (b / bpc) * ld_c + (b % bpc) * R;
-        for (int k0 = 0; k0 < N; k0 += kDirectKB) {
-            double aq[kDirectKB], ai[kDirectKB];
-#pragma unroll
-            for (int kk = 0; kk < kDirectKB; ++kk) aq[kk] = ai[kk] = 0.0;
+struct DirectParams {
+    const double* x;
+    long long nbuf, bpc, ld_c, R;
+    int N;
+    double w0;
+    double* qi;
+    double* dc;
+    int steps;  // table length: 32 * steps samples per chunk
+};
+
+template <int KB, bool MULTI, int THREADS = kDirectThreads>
+__global__ void __launch_bounds__(THREADS) demod_direct_kernel(const DirectParams p) {
+    constexpr int kDirectThreads = THREADS;  // (a big table leaves room for one CTA per SM: it then brings more warps)
+    extern __shared__ __align__(16) unsigned char direct_smem[];
+    double2* tab = reinterpret_cast<double2*>(direct_smem);                  // [steps][KB]: cos, sin of w_k 32 j
+    double2* lane_tab = tab + static_cast<size_t>(p.steps) * KB;             // [KB][32]:    cos, sin of w_k l
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * kDirectThreads + tid) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * kDirectThreads) >> 5;
+    const long long R = p.R;
+    const double inv_r = 1.0 / static_cast<double>(R);
+    for (int k0 = 0; k0 < p.N; k0 += KB) {
+        __syncthreads();  // the previous pass is done with the tables
+        for (int i = tid; i < p.steps * KB; i += kDirectThreads) {
+            const int j = i / KB, kk = i - j * KB;
+            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;  // fl((k + 1) * w0), fit.py:59
+            double sv, cv;
+            sincos(wk * static_cast<double>(32 * j), &sv, &cv);
+            tab[i] = make_double2(cv, sv);
+        }
+        for (int i = tid; i < KB * 32; i += kDirectThreads) {
+            const int kk = i >> 5, l = i & 31;
+            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
+            double sv, cv;
+            sincos(wk * static_cast<double>(l), &sv, &cv);
+            lane_tab[i] = make_double2(cv, sv);
+        }
+        __syncthreads();
+        for (long long b = warp; b < p.nbuf; b += nwarps) {
+            const double* buf = p.x + (b / p.bpc) * p.ld_c + (b % p.bpc) * R;
+            double q[MULTI ? KB : 1], iv[MULTI ? KB : 1];
+            double sc[KB], ss[KB];
             double asum = 0.0;
-            for (long long t0 = tid; t0 < R; t0 += static_cast<long long>(kDirectThreads) * kDirectResync) {
-                double c[kDirectKB], s[kDirectKB], cs[kDirectKB], ss[kDirectKB];
 #pragma unroll
-                for (int kk = 0; kk < kDirectKB; ++kk) {
-                    // the reference forms the angle as fl(fl((k)*w0) * t)  (fit.py:59)
-                    const double wk = static_cast<double>(k0 + kk + 1) * w0;
-                    sincos(wk * static_cast<double>(t0), &s[kk], &c[kk]);
-                    sincos(wk * static_cast<double>(kDirectThreads), &ss[kk], &cs[kk]);
+            for (int kk = 0; kk < KB; ++kk) {
+                sc[kk] = ss[kk] = 0.0;
+                if (MULTI) q[kk] = iv[kk] = 0.0;
+            }
+            for (long long c0 = 0; c0 < R; c0 += 32ll * p.steps) {
+                const long long left = R - c0;
+                const int full = static_cast<int>(left >= 32ll * p.steps ? p.steps : left >> 5);  // steps with all 32 lanes
+                const double* src = buf + c0 + lane;
+                int j = 0;
+                for (; j + 4 <= full; j += 4) {  // four loads in flight per lane
+                    double v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = __ldg(src + 32 * (j + e));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        asum += v[e];
+                        const double2* row = tab + static_cast<size_t>(j + e) * KB;
+#pragma unroll
+                        for (int kk = 0; kk < KB; ++kk) {
+                            const double2 w = row[kk];
+                            sc[kk] = fma(v[e], w.x, sc[kk]);
+                            ss[kk] = fma(v[e], w.y, ss[kk]);
+                        }
+                    }
                 }
-                long long t = t0;
-                for (int i = 0; i < kDirectResync && t < R; ++i, t += kDirectThreads) {
-                    const double v = __ldg(buf + t);
+                const int last = static_cast<int>(left >= 32ll * p.steps ? p.steps : (left + 31) >> 5);
+                for (; j < last; ++j) {  // the remaining whole steps and the ragged one
+                    const double v = (c0 + lane + 32ll * j < R) ? __ldg(src + 32 * j) : 0.0;
                     asum += v;
+                    const double2* row = tab + static_cast<size_t>(j) * KB;
 #pragma unroll
-                    for (int kk = 0; kk < kDirectKB; ++kk) {
-                        aq[kk] = fma(v, c[kk], aq[kk]);
-                        ai[kk] = fma(v, s[kk], ai[kk]);
-                        const double cn = c[kk] * cs[kk] - s[kk] * ss[kk];
-                        s[kk] = fma(s[kk], cs[kk], c[kk] * ss[kk]);
-                        c[kk] = cn;
+                    for (int kk = 0; kk < KB; ++kk) {
+                        const double2 w = row[kk];
+                        sc[kk] = fma(v, w.x, sc[kk]);
+                        ss[kk] = fma(v, w.y, ss[kk]);
+                    }
+                }
+                // rotate the chunk's sums by w_k (c0 + lane): cos(a + b) = ca cb - sa sb, sin(a + b) = sa cb + ca sb
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk) {
+                    double ca, sa;
+                    if (!MULTI || c0 == 0) {
+                        const double2 w = lane_tab[kk * 32 + lane];
+                        ca = w.x;
+                        sa = w.y;
+                    } else {
+                        const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
+                        sincos(wk * static_cast<double>(c0 + lane), &sa, &ca);
+                    }
+                    const double qr = ca * sc[kk] - sa * ss[kk];
+                    const double ir = sa * sc[kk] + ca * ss[kk];
+                    if (MULTI) {
+                        q[kk] += qr;
+                        iv[kk] += ir;
+                        sc[kk] = ss[kk] = 0.0;
+                    } else {
+                        sc[kk] = qr;
+                        ss[kk] = ir;
                     }
                 }
             }
 #pragma unroll
-            for (int kk = 0; kk < kDirectKB; ++kk) {
-                aq[kk] = warp_sum(aq[kk]);
-                ai[kk] = warp_sum(ai[kk]);
-            }
-            asum = warp_sum(asum);
-            __syncthreads();
-            if (lane == 0) {
-#pragma unroll
-                for (int kk = 0; kk < kDirectKB; ++kk) {
-                    red[warp][kk] = aq[kk];
-                    red[warp][kDirectKB + kk] = ai[kk];
+            for (int kk = 0; kk < KB; ++kk) {
+                const double qs = warp_sum(MULTI ? q[kk] : sc[kk]);
+                const double is = warp_sum(MULTI ? iv[kk] : ss[kk]);
+                if (lane == 0 && k0 + kk < p.N) {
+                    p.qi[b * 2 * p.N + k0 + kk] = qs * inv_r;
+                    p.qi[b * 2 * p.N + p.N + k0 + kk] = is * inv_r;
                 }
-                red[warp][2 * kDirectKB] = asum;
             }
-            __syncthreads();
-            if (tid <= 2 * kDirectKB) {
-                double v = 0.0;
-#pragma unroll
-                for (int w = 0; w < kDirectThreads / 32; ++w) v += red[w][tid];
-                v /= static_cast<double>(R);
-                if (tid == 2 * kDirectKB) {
-                    if (k0 == 0) dc[b] = v;
-                } else {
-                    const int kk = tid % kDirectKB;
-                    if (k0 + kk < N) qi[b * 2 * N + (tid < kDirectKB ? 0 : N) + k0 + kk] = v;
-                }
+            if (k0 == 0) {
+                asum = warp_sum(asum);
+                if (lane == 0) p.dc[b] = asum * inv_r;
             }
         }
     }

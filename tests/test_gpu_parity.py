@@ -705,3 +705,28 @@ def test_time_major_demod_matches_reference_lockin(torch_mod, ctx, P, n, nh, C, 
             ref = orc.lockin_means(buf, w0, nh)
             assert np.max(np.abs(qi[c, b] - ref)) <= IQ_TOL * max(np.abs(ref).max(), 1e-3), (c, b)
             assert abs(dc[c, b] - buf.mean()) <= 1e-14 * abs(buf.mean())
+
+
+@pytest.mark.parametrize("R,nh,f_mod", [(3240, 10, 1234.5), (3241, 8, 1234.5), (5, 3, 1234.5), (31, 12, 977.7), (33, 16, 977.7),
+                                        (4097, 40, 1234.5), (1000, 64, 977.7), (300_001, 10, 1234.5),
+                                        (700_000, 20, 1001.3), (64, 1, 1234.5)])
+def test_direct_lockin_shapes(torch_mod, ctx, R, nh, f_mod):
+    """Records that cannot fold (incommensurate modulation period) through the table-driven lock-in: buffers shorter
+    than a warp, ragged last steps, 8 / 12 / 16 harmonics per pass, several passes (N = 20, 40, 64), buffers longer
+    than one table chunk (300 001 and 700 000 samples), against the reference's own formulation (oracle)."""
+    from deepfmkit_b200 import _lib
+    f_samp = 200e3
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    assert _lib.demod_path(R, w0) == 0
+    nbuf = 19 if R < 100_000 else 3
+    rng = np.random.RandomState(R + nh)
+    t = np.arange(nbuf * R)
+    x = 1.0 + np.cos(0.4 + 5.0 * np.cos(w0 * t + 0.3)) + 0.01 * rng.randn(nbuf * R)
+    qi, dc = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    worst = 0.0
+    for b in range(nbuf):
+        buf = x[b * R:(b + 1) * R]
+        ref = orc.lockin_means(buf, w0, nh)
+        worst = max(worst, np.max(np.abs(qi[b] - ref)) / max(np.abs(ref).max(), 1e-3))
+        assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
+    assert worst <= IQ_TOL, worst
