@@ -144,9 +144,18 @@ class Experiment:
                                           if k in self._expected_params_keys or k.startswith("_exp_")}
                 counter += self.n_trials if first_trial_only else 1
 
-    def run(self, n_cores: Optional[int] = None, filename: Optional[str] = None, device: int = 0,
-            max_resident_bytes: int = 8 << 30) -> Dict[str, Any]:
+    def run(self, n_cores: Optional[int] = None, filename: Optional[str] = None, device: Optional[int] = None,
+            max_resident_bytes: int = 8 << 30, group=None) -> Dict[str, Any]:
         import torch
+        # group: a torch.distributed process group (one process per GPU).  Grid points are independent, so they are cut
+        # into contiguous ranges, one per rank; nothing crosses the GPUs but the finished per-point tables, gathered as
+        # Python objects at the end (every rank returns the full result).  Trial numbers -- the noise keys -- are those
+        # of the one-GPU run, so the result does not depend on the number of ranks.
+        rank, world = 0, 1
+        if group is not None:
+            rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        if device is None:
+            device = torch.cuda.current_device() if world > 1 else 0
         if self.config_factory is None:
             raise ValueError("A configuration factory must be set using set_config_factory().")
         if not self.axes and not self.n_trials > 0:
@@ -198,6 +207,10 @@ class Experiment:
                 records[counter], df_of[counter] = pack(params, counter)
 
         # ---- 2. simulate and fit in waves ----------------------------------------------------------------------------
+        from .sharding import slab_bounds
+        p_lo, p_hi = slab_bounds(npoints, world, rank) if world > 1 else (0, npoints)
+        records, df_of = records[p_lo * ntr:p_hi * ntr], df_of[p_lo * ntr:p_hi * ntr]
+        npoints_all, npoints = npoints, p_hi - p_lo
         dev = torch.device("cuda", device)
         ctx = _lib.get_context(device)
         J = records.shape[0]
@@ -209,6 +222,7 @@ class Experiment:
         values = {a["name"]: torch.full((J, len(RESULT_KEYS)), float("nan"), dtype=torch.float64, device=dev)
                   for a in self.analyses}
         with torch.cuda.device(dev):
+            per_wave = max(per_wave, 1)
             y = torch.empty((per_wave, n_samples), dtype=torch.float64, device=dev)
             rows = torch.empty((per_wave, max(nbuf, 1), _lib.ROW_STRIDE), dtype=torch.float64, device=dev)
             df_dev = torch.from_numpy(df_of).to(dev)
@@ -239,30 +253,40 @@ class Experiment:
                     v[lo:hi, :7] = r
                     v[lo:hi, 7] = r[:, 1] / (2.0 * np.pi * df_dev[lo:hi])  # tau (core.py:506-507)
             # ---- 3. grid statistics on the device ------------------------------------------------------------------
-            results: Dict[str, Any] = {"axes": self.axes}
+            local = {}
             for a in self.analyses:
                 v = values[a["name"]]
                 stats = torch.empty((npoints, len(RESULT_KEYS), _lib.TRIAL_STATS_DOUBLES), dtype=torch.float64, device=dev)
-                ctx.use_torch_stream()
-                try:
-                    ctx.trial_stats_dev(v.data_ptr(), npoints, ntr, len(RESULT_KEYS), len(RESULT_KEYS), stats.data_ptr())
-                finally:
-                    ctx.use_default_stream()
-                st = stats.cpu().numpy()
-                allv = v.cpu().numpy().reshape(grid_shape + (ntr, len(RESULT_KEYS)))
-                cols = a.get("result_cols") or sorted(RESULT_KEYS)
-                out = {}
-                for col in cols:
-                    if col not in RESULT_KEYS:
-                        grid = np.full(grid_shape + (ntr,), np.nan)
-                        out[col] = {"all_trials": grid, **{k: np.full(grid_shape, np.nan) for k in ("mean", "std", "min", "max", "worst")}}
-                        continue
-                    c = RESULT_KEYS.index(col)
-                    d = {"all_trials": np.ascontiguousarray(allv[..., c])}
-                    for k, name in enumerate(("mean", "std", "min", "max", "worst")):
-                        d[name] = st[:, c, k].reshape(grid_shape) if grid_shape else st[0, c, k]
-                    out[col] = d
-                results[a["name"]] = out
+                if npoints:
+                    ctx.use_torch_stream()
+                    try:
+                        ctx.trial_stats_dev(v.data_ptr(), npoints, ntr, len(RESULT_KEYS), len(RESULT_KEYS), stats.data_ptr())
+                    finally:
+                        ctx.use_default_stream()
+                local[a["name"]] = (stats.cpu().numpy(), v.cpu().numpy().reshape(npoints, ntr, len(RESULT_KEYS)))
+        if world > 1:
+            parts = [None] * world
+            torch.distributed.all_gather_object(parts, local, group=group)
+        else:
+            parts = [local]
+        results: Dict[str, Any] = {"axes": self.axes}
+        for a in self.analyses:
+            st = np.concatenate([p[a["name"]][0] for p in parts], axis=0)
+            allv = np.concatenate([p[a["name"]][1] for p in parts], axis=0).reshape(grid_shape + (ntr, len(RESULT_KEYS)))
+            assert st.shape[0] == npoints_all
+            cols = a.get("result_cols") or sorted(RESULT_KEYS)
+            out = {}
+            for col in cols:
+                if col not in RESULT_KEYS:
+                    grid = np.full(grid_shape + (ntr,), np.nan)
+                    out[col] = {"all_trials": grid, **{k: np.full(grid_shape, np.nan) for k in ("mean", "std", "min", "max", "worst")}}
+                    continue
+                c = RESULT_KEYS.index(col)
+                d = {"all_trials": np.ascontiguousarray(allv[..., c])}
+                for k, name in enumerate(("mean", "std", "min", "max", "worst")):
+                    d[name] = st[:, c, k].reshape(grid_shape) if grid_shape else st[0, c, k]
+                out[col] = d
+            results[a["name"]] = out
         self.results = results
         if filename is not None:
             self.save_results(filename)

@@ -528,10 +528,11 @@ def test_synth_statistics(torch_mod, ctx):
 
 
 @pytest.mark.parametrize("script,token,port", [("sharded_record.py", "SHARDED_OK", 29577),
-                                               ("sharded_sweep.py", "SWEEP_OK", 29578)])
+                                               ("sharded_sweep.py", "SWEEP_OK", 29578),
+                                               ("sharded_experiment.py", "EXPERIMENT_OK", 29579)])
 def test_sharded_over_gpus(torch_mod, script, token, port):
-    """One record cut into contiguous slabs / one Monte-Carlo sweep split by realisation over all visible GPUs
-    (torchrun, nccl) == the one-GPU result."""
+    """One record cut into contiguous slabs / one Monte-Carlo sweep split by realisation / one Experiment split by grid
+    point over all visible GPUs (torchrun, nccl) == the one-GPU result."""
     import subprocess
     import sys
     n = torch_mod.cuda.device_count()
