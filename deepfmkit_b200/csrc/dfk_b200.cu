@@ -265,11 +265,27 @@ int launch_direct_tt(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, int 
     return DFK_OK;
 }
 
+template <int KB, int THREADS>
+int launch_direct_pair(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, cudaStream_t st) {
+    auto kernel = dfk::demod_direct_pair_kernel<KB, THREADS>;
+    DFK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t warps_per_cta = THREADS / 32, npairs = (q.nbuf + 1) / 2;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((npairs + warps_per_cta - 1) / warps_per_cta,
+                                                                            static_cast<int64_t>(ctx->sm_count))));
+    kernel<<<grid, THREADS, smem, st>>>(q);
+    return DFK_OK;
+}
+
 template <int KB, bool MULTI>
 int launch_direct_t(dfk_ctx* ctx, const dfk::DirectParams& p, int steps, cudaStream_t st) {
     dfk::DirectParams q = p;
     q.steps = steps;
     const size_t smem = (static_cast<size_t>(steps) * KB + static_cast<size_t>(KB) * 32) * sizeof(double2);
+    // enough buffers to give every warp of the GPU a pair: two buffers per warp (registers: one CTA of 12 warps per SM)
+    if constexpr (!MULTI && KB <= 10) {
+        if (q.nbuf >= 2 * 12 * static_cast<int64_t>(ctx->sm_count) && dev_int("DFK_DIRECT_PAIR", 1))
+            return launch_direct_pair<KB, 384>(ctx, q, smem, st);
+    }
     const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, static_cast<size_t>(ctx->smem_per_sm) / (smem + 1024))));
     // one CTA per SM (a long table): 512 threads, which the 128 registers of the narrower builds allow
     if (per_sm == 1 && KB <= 12 && !MULTI && dev_int("DFK_DIRECT_THREADS", 512) == 512)

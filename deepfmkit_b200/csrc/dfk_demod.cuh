@@ -1396,4 +1396,115 @@ __global__ void __launch_bounds__(THREADS) demod_direct_kernel(const DirectParam
     }
 }
 
+// Two buffers per warp (single-chunk buffers only).  ncu puts the one-buffer kernel at 87 % of the LSU data pipe: a
+// broadcast LDS.128 still writes 512 B of registers per warp, ten of them per step.  A table entry fetched once here
+// serves both buffers, which halves that traffic at twice the accumulators; four steps of both buffers are loaded
+// ahead (with two, the 12 warps per SM the registers allow capped the bytes in flight: 2.4 TB/s).
+// Buffers b and b + 1 of a pair are adjacent in the launch's numbering; an odd last one goes alone.
+template <int KB, int THREADS>
+__global__ void __launch_bounds__(THREADS) demod_direct_pair_kernel(const DirectParams p) {
+    extern __shared__ __align__(16) unsigned char direct_smem[];
+    double2* tab = reinterpret_cast<double2*>(direct_smem);
+    double2* lane_tab = tab + static_cast<size_t>(p.steps) * KB;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * THREADS + tid) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * THREADS) >> 5;
+    const long long R = p.R;
+    const double inv_r = 1.0 / static_cast<double>(R);
+    const long long npairs = (p.nbuf + 1) >> 1;
+    constexpr int U = 4;
+    for (int k0 = 0; k0 < p.N; k0 += KB) {
+        __syncthreads();
+        for (int i = tid; i < p.steps * KB; i += THREADS) {
+            const int j = i / KB, kk = i - j * KB;
+            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
+            double sv, cv;
+            sincos(wk * static_cast<double>(32 * j), &sv, &cv);
+            tab[i] = make_double2(cv, sv);
+        }
+        for (int i = tid; i < KB * 32; i += THREADS) {
+            const int kk = i >> 5, l = i & 31;
+            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
+            double sv, cv;
+            sincos(wk * static_cast<double>(l), &sv, &cv);
+            lane_tab[i] = make_double2(cv, sv);
+        }
+        __syncthreads();
+        for (long long pr = warp; pr < npairs; pr += nwarps) {
+            const long long b0 = 2 * pr, b1 = (2 * pr + 1 < p.nbuf) ? 2 * pr + 1 : 2 * pr;  // (an odd tail reads itself twice)
+            const double* src0 = p.x + (b0 / p.bpc) * p.ld_c + (b0 % p.bpc) * R + lane;
+            const double* src1 = p.x + (b1 / p.bpc) * p.ld_c + (b1 % p.bpc) * R + lane;
+            double sc0[KB], ss0[KB], sc1[KB], ss1[KB];
+            double asum0 = 0.0, asum1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) sc0[kk] = ss0[kk] = sc1[kk] = ss1[kk] = 0.0;
+            const int full = static_cast<int>(R >> 5);
+            int j = 0;
+            for (; j + U <= full; j += U) {
+                double v0[U], v1[U];
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    v0[e] = __ldg(src0 + 32 * (j + e));
+                    v1[e] = __ldg(src1 + 32 * (j + e));
+                }
+#pragma unroll
+                for (int e = 0; e < U; ++e) {
+                    asum0 += v0[e];
+                    asum1 += v1[e];
+                    const double2* row = tab + static_cast<size_t>(j + e) * KB;
+#pragma unroll
+                    for (int kk = 0; kk < KB; ++kk) {
+                        const double2 w = row[kk];
+                        sc0[kk] = fma(v0[e], w.x, sc0[kk]);
+                        ss0[kk] = fma(v0[e], w.y, ss0[kk]);
+                        sc1[kk] = fma(v1[e], w.x, sc1[kk]);
+                        ss1[kk] = fma(v1[e], w.y, ss1[kk]);
+                    }
+                }
+            }
+            const int last = static_cast<int>((R + 31) >> 5);
+            for (; j < last; ++j) {
+                const bool in = lane + 32ll * j < R;
+                const double v0 = in ? __ldg(src0 + 32 * j) : 0.0;
+                const double v1 = in ? __ldg(src1 + 32 * j) : 0.0;
+                asum0 += v0;
+                asum1 += v1;
+                const double2* row = tab + static_cast<size_t>(j) * KB;
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk) {
+                    const double2 w = row[kk];
+                    sc0[kk] = fma(v0, w.x, sc0[kk]);
+                    ss0[kk] = fma(v0, w.y, ss0[kk]);
+                    sc1[kk] = fma(v1, w.x, sc1[kk]);
+                    ss1[kk] = fma(v1, w.y, ss1[kk]);
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+                const double2 w = lane_tab[kk * 32 + lane];
+                const double q0 = warp_sum(w.x * sc0[kk] - w.y * ss0[kk]);
+                const double i0 = warp_sum(w.y * sc0[kk] + w.x * ss0[kk]);
+                const double q1 = warp_sum(w.x * sc1[kk] - w.y * ss1[kk]);
+                const double i1 = warp_sum(w.y * sc1[kk] + w.x * ss1[kk]);
+                if (lane == 0 && k0 + kk < p.N) {
+                    p.qi[b0 * 2 * p.N + k0 + kk] = q0 * inv_r;
+                    p.qi[b0 * 2 * p.N + p.N + k0 + kk] = i0 * inv_r;
+                    if (b1 != b0) {
+                        p.qi[b1 * 2 * p.N + k0 + kk] = q1 * inv_r;
+                        p.qi[b1 * 2 * p.N + p.N + k0 + kk] = i1 * inv_r;
+                    }
+                }
+            }
+            if (k0 == 0) {
+                asum0 = warp_sum(asum0);
+                asum1 = warp_sum(asum1);
+                if (lane == 0) {
+                    p.dc[b0] = asum0 * inv_r;
+                    if (b1 != b0) p.dc[b1] = asum1 * inv_r;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace dfk

@@ -731,3 +731,26 @@ def test_direct_lockin_shapes(torch_mod, ctx, R, nh, f_mod):
         worst = max(worst, np.max(np.abs(qi[b] - ref)) / max(np.abs(ref).max(), 1e-3))
         assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
     assert worst <= IQ_TOL, worst
+
+
+@pytest.mark.parametrize("R,nh", [(517, 10), (4000, 7), (64, 9)])
+def test_direct_lockin_pairs(torch_mod, ctx, R, nh):
+    """With enough buffers the table-driven lock-in takes two per warp: same numbers as one per warp (the per-lane
+    order of operations is the same), an odd last buffer included, and the oracle's on a sample of them."""
+    from deepfmkit_b200 import _lib
+    f_samp, f_mod = 200e3, 1234.5
+    w0 = orc.rad_per_sample(f_samp, f_mod)
+    assert _lib.demod_path(R, w0) == 0
+    nbuf = 2 * 12 * 160 + 1
+    rng = np.random.RandomState(R)
+    t = np.arange(nbuf * R)
+    x = 1.0 + np.cos(0.4 + 5.0 * np.cos(w0 * t + 0.3)) + 0.01 * rng.randn(nbuf * R)
+    qi, dc = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    with _lib.dev_overrides(DFK_DIRECT_PAIR=0):
+        qi1, dc1 = gpu_demod(torch_mod, ctx, x, R, nh, w0)
+    assert np.array_equal(qi, qi1) and np.array_equal(dc, dc1)
+    for b in list(range(0, nbuf, 397)) + [nbuf - 2, nbuf - 1]:
+        buf = x[b * R:(b + 1) * R]
+        ref = orc.lockin_means(buf, w0, nh)
+        assert np.max(np.abs(qi[b] - ref)) <= IQ_TOL * np.abs(ref).max(), b
+        assert abs(dc[b] - buf.mean()) <= 1e-14 * abs(buf.mean())
