@@ -252,14 +252,14 @@ int try_launch_tile(dfk_ctx* ctx, const dfk::DemodPlan& pl, const double* x, int
 
 // nbuf buffers in channel records of bpc buffers each, records ld_c samples apart
 // leave_room: keep enough shared memory free on each SM for a block of the seed fits that run beside this launch
-// Records that do not fold (dfk_demod.cuh, demod_direct_kernel): a warp per buffer, 8 or 16 harmonics per pass, the
-// step table sized to the buffer when it fits beside a second CTA, else to what one CTA may hold.
-template <int KB, bool MULTI, int THREADS>
-int launch_direct_tt(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, int per_sm, cudaStream_t st) {
-    auto kernel = dfk::demod_direct_kernel<KB, MULTI, THREADS>;
+// Records that do not fold (dfk_demod.cuh, demod_direct_kernel): a warp per piece (two when there are enough), 8 to 16
+// harmonics per pass; a piece is the buffer when a CTA's table can hold its steps, else a 16 384-sample chunk of it.
+template <int KB, int THREADS>
+int launch_direct_one(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, int per_sm, cudaStream_t st) {
+    auto kernel = dfk::demod_direct_kernel<KB, THREADS>;
     DFK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int64_t warps_per_cta = THREADS / 32;
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((q.nbuf + warps_per_cta - 1) / warps_per_cta,
+    const int64_t warps_per_cta = THREADS / 32, npieces = q.nbuf * q.cpb;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((npieces + warps_per_cta - 1) / warps_per_cta,
                                                                             static_cast<int64_t>(ctx->sm_count) * per_sm)));
     kernel<<<grid, THREADS, smem, st>>>(q);
     return DFK_OK;
@@ -269,53 +269,62 @@ template <int KB, int THREADS>
 int launch_direct_pair(dfk_ctx* ctx, const dfk::DirectParams& q, size_t smem, cudaStream_t st) {
     auto kernel = dfk::demod_direct_pair_kernel<KB, THREADS>;
     DFK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int64_t warps_per_cta = THREADS / 32, npairs = (q.nbuf + 1) / 2;
+    const int64_t warps_per_cta = THREADS / 32, npairs = (q.nbuf * q.cpb + 1) / 2;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((npairs + warps_per_cta - 1) / warps_per_cta,
                                                                             static_cast<int64_t>(ctx->sm_count))));
     kernel<<<grid, THREADS, smem, st>>>(q);
     return DFK_OK;
 }
 
-template <int KB, bool MULTI>
-int launch_direct_t(dfk_ctx* ctx, const dfk::DirectParams& p, int steps, cudaStream_t st) {
-    dfk::DirectParams q = p;
-    q.steps = steps;
-    const size_t smem = (static_cast<size_t>(steps) * KB + static_cast<size_t>(KB) * 32) * sizeof(double2);
-    // enough buffers to give every warp of the GPU a pair: two buffers per warp (registers: one CTA of 12 warps per SM)
-    if constexpr (!MULTI && KB <= 10) {
-        if (q.nbuf >= 2 * 12 * static_cast<int64_t>(ctx->sm_count) && dev_int("DFK_DIRECT_PAIR", 1))
+template <int KB>
+int launch_direct_t(dfk_ctx* ctx, const dfk::DirectParams& q, cudaStream_t st) {
+    const size_t smem = (static_cast<size_t>(q.steps) * KB + static_cast<size_t>(KB) * 32) * sizeof(double2);
+    // enough pieces to give every warp of the GPU a pair: two per warp (registers: one CTA of 12 warps per SM)
+    if constexpr (KB <= 10) {
+        if (q.nbuf * q.cpb >= 2 * 12 * static_cast<int64_t>(ctx->sm_count) && dev_int("DFK_DIRECT_PAIR", 1))
             return launch_direct_pair<KB, 384>(ctx, q, smem, st);
     }
     const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, static_cast<size_t>(ctx->smem_per_sm) / (smem + 1024))));
     // one CTA per SM (a long table): 512 threads, which the 128 registers of the narrower builds allow
-    if (per_sm == 1 && KB <= 12 && !MULTI && dev_int("DFK_DIRECT_THREADS", 512) == 512)
-        return launch_direct_tt<KB, MULTI, 512>(ctx, q, smem, per_sm, st);
-    return launch_direct_tt<KB, MULTI, dfk::kDirectThreads>(ctx, q, smem, per_sm, st);
+    if constexpr (KB <= 12) {
+        if (per_sm == 1 && dev_int("DFK_DIRECT_THREADS", 512) == 512) return launch_direct_one<KB, 512>(ctx, q, smem, per_sm, st);
+    }
+    return launch_direct_one<KB, dfk::kDirectThreads>(ctx, q, smem, per_sm, st);
 }
 
 int launch_direct(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int N, double w0,
                   double* qi, double* dc, cudaStream_t st) {
-    dfk::DirectParams p = {x, nbuf, bpc, ld_c, R, N, w0, qi, dc, 0};
+    dfk::DirectParams p = {x, nbuf, bpc, ld_c, R, N, w0, qi, dc, 0, 1, nullptr};
     const int64_t need = (R + 31) / 32;  // steps that cover a buffer
     const size_t budget = static_cast<size_t>(ctx->max_smem_optin) - 2048;
     // harmonics per pass: the narrow builds run twice as fast per pass as the 16-wide one (registers: one CTA of eight
     // warps per SM), so beyond 16 harmonics several passes of 10 or 12 beat fewer of 16
     int kb = N <= 8 ? 8 : (N <= 10 ? 10 : (N <= 12 ? 12 : 16));
     if (N > 16) kb = (N + 11) / 12 < (N + 9) / 10 ? 12 : 10;
-    const int64_t fit1 = static_cast<int64_t>(budget / sizeof(double2) / kb) - 32;
-    if (need <= fit1) {  // the whole buffer in one chunk
-        const int steps = static_cast<int>(need);
-        switch (kb) {
-            case 8: return launch_direct_t<8, false>(ctx, p, steps, st);
-            case 10: return launch_direct_t<10, false>(ctx, p, steps, st);
-            case 12: return launch_direct_t<12, false>(ctx, p, steps, st);
-            default: return launch_direct_t<16, false>(ctx, p, steps, st);
-        }
+    const int64_t fit = static_cast<int64_t>(budget / sizeof(double2) / kb) - 32;
+    if (need <= fit) {
+        p.steps = static_cast<int>(need);
+    } else {  // long buffers: 16 384-sample chunks, their sums combined afterwards
+        p.steps = static_cast<int>(std::min<int64_t>(512, fit));
+        p.cpb = (need + p.steps - 1) / p.steps;
+        const int rc = ensure(ctx, ctx->post[6], static_cast<size_t>(nbuf) * p.cpb * (2 * N + 1) * sizeof(double));
+        if (rc) return rc;
+        p.part = static_cast<double*>(ctx->post[6].ptr);
     }
-    // long buffers: chunks of what a CTA's table holds, eight harmonics per pass (the chunk sums need a second set of
-    // accumulators)
-    const int64_t fit8 = static_cast<int64_t>(budget / sizeof(double2) / 8) - 32;
-    return launch_direct_t<8, true>(ctx, p, static_cast<int>(std::min<int64_t>(need, fit8)), st);
+    int rc;
+    switch (kb) {
+        case 8: rc = launch_direct_t<8>(ctx, p, st); break;
+        case 10: rc = launch_direct_t<10>(ctx, p, st); break;
+        case 12: rc = launch_direct_t<12>(ctx, p, st); break;
+        default: rc = launch_direct_t<16>(ctx, p, st); break;
+    }
+    if (rc) return rc;
+    if (p.cpb > 1) {
+        const int64_t n = nbuf * (N + 1);
+        dfk::direct_combine_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(p);
+        ctx->launches++;
+    }
+    return DFK_OK;
 }
 
 int launch_demod(dfk_ctx* ctx, const double* x, int64_t nbuf, int64_t bpc, int64_t ld_c, int64_t R, int32_t N, double w0,

@@ -1262,13 +1262,16 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) demod_period_kernel(const
 // ---------------------------------------------------------------------------------------------------
 // Lock-in for records that cannot fold (the modulation period is not a small rational number of samples, or the
 // buffer is not whole fold lengths): every sample meets every harmonic, cos/sin of fl(w_k t) as the reference forms
-// them (fit.py:55-64).  Lane l of a warp takes the samples t = c0 + l + 32 j of a buffer, so that
-//     w_k t = w_k (c0 + l) + w_k 32 j,
-// the second term being the same for every lane and every buffer: its cos/sin for j < steps live in a shared-memory
+// them (fit.py:55-64).  Lane l of a warp takes the samples t = l + 32 j of a piece, so that
+//     w_k t = w_k l + w_k 32 j,
+// the second term being the same for every lane and every piece: its cos/sin for j < steps live in a shared-memory
 // table built once per launch (read as broadcasts), and a sample costs its load plus two FMAs per harmonic.  The
-// lane's sums are rotated by w_k (c0 + l) at the end of the chunk -- from a second small table for the first chunk,
-// which is the whole buffer unless it is longer than 32 * steps samples -- then reduced over the warp.
-// KB harmonics per pass over the record (N > KB re-reads it); MULTI: buffers of several chunks.
+// lane's sums are rotated by w_k l at the end (a second, 32-entry table), then reduced over the warp.
+// A piece is a whole buffer when it fits a table (32 * steps samples), else one of its chunks of that length: the
+// chunk sums, taken with t counted from the chunk's start, go to scratch and direct_combine_kernel rotates each by
+// w_k c0 (its own sincos: nothing accumulates along the buffer) and adds them up in order -- so a few very long
+// buffers spread over the whole GPU like many short ones.
+// KB harmonics per pass over the record (N > KB re-reads it).
 // Rotating term by term instead (the first version of this kernel: one complex rotation per sample and harmonic, two
 // sincos per 64 samples to stop its drift) spent 7 fp64 operations where this one spends 2: 0.34 TB/s.
 // ---------------------------------------------------------------------------------------------------
@@ -1281,126 +1284,123 @@ struct DirectParams {
     double w0;
     double* qi;
     double* dc;
-    int steps;  // table length: 32 * steps samples per chunk
+    int steps;          // table length: pieces of up to 32 * steps samples
+    long long cpb;      // pieces (chunks) per buffer; 1: a piece is the buffer, results go straight to qi / dc
+    double* part;       // cpb > 1: [nbuf * cpb][2 N + 1] rotated, un-normalised chunk sums and the chunk's plain sum
 };
 
-template <int KB, bool MULTI, int THREADS = kDirectThreads>
+// piece v of the launch: where it starts and how long it is
+DFK_D const double* direct_piece(const DirectParams& p, long long v, long long& len) {
+    const long long b = v / p.cpb, c = v - b * p.cpb;
+    const long long L = 32ll * p.steps;
+    len = p.cpb == 1 ? p.R : (p.R - c * L < L ? p.R - c * L : L);
+    return p.x + (b / p.bpc) * p.ld_c + (b % p.bpc) * p.R + c * L;
+}
+
+DFK_D void direct_build_tables(const DirectParams& p, int k0, int KB, double2* tab, double2* lane_tab, int tid, int nthreads) {
+    for (int i = tid; i < p.steps * KB; i += nthreads) {
+        const int j = i / KB, kk = i - j * KB;
+        const double wk = static_cast<double>(k0 + kk + 1) * p.w0;  // fl((k + 1) * w0), fit.py:59
+        double sv, cv;
+        sincos(wk * static_cast<double>(32 * j), &sv, &cv);
+        tab[i] = make_double2(cv, sv);
+    }
+    for (int i = tid; i < KB * 32; i += nthreads) {
+        const int kk = i >> 5, l = i & 31;
+        const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
+        double sv, cv;
+        sincos(wk * static_cast<double>(l), &sv, &cv);
+        lane_tab[i] = make_double2(cv, sv);
+    }
+}
+
+// lane 0 stores harmonic k0 + kk of piece v: normalised into qi when the piece is the buffer, else raw into scratch
+DFK_D void direct_store(const DirectParams& p, long long v, int k, double q, double i, double inv_r) {
+    if (p.cpb == 1) {
+        p.qi[v * 2 * p.N + k] = q * inv_r;
+        p.qi[v * 2 * p.N + p.N + k] = i * inv_r;
+    } else {
+        p.part[v * (2 * p.N + 1) + k] = q;
+        p.part[v * (2 * p.N + 1) + p.N + k] = i;
+    }
+}
+DFK_D void direct_store_sum(const DirectParams& p, long long v, double sum, double inv_r) {
+    if (p.cpb == 1) p.dc[v] = sum * inv_r;
+    else p.part[v * (2 * p.N + 1) + 2 * p.N] = sum;
+}
+
+template <int KB, int THREADS = kDirectThreads>
 __global__ void __launch_bounds__(THREADS) demod_direct_kernel(const DirectParams p) {
-    constexpr int kDirectThreads = THREADS;  // (a big table leaves room for one CTA per SM: it then brings more warps)
     extern __shared__ __align__(16) unsigned char direct_smem[];
     double2* tab = reinterpret_cast<double2*>(direct_smem);                  // [steps][KB]: cos, sin of w_k 32 j
     double2* lane_tab = tab + static_cast<size_t>(p.steps) * KB;             // [KB][32]:    cos, sin of w_k l
     const int tid = threadIdx.x, lane = tid & 31;
-    const long long warp = (static_cast<long long>(blockIdx.x) * kDirectThreads + tid) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * kDirectThreads) >> 5;
-    const long long R = p.R;
-    const double inv_r = 1.0 / static_cast<double>(R);
+    const long long warp = (static_cast<long long>(blockIdx.x) * THREADS + tid) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * THREADS) >> 5;
+    const double inv_r = 1.0 / static_cast<double>(p.R);
+    const long long npieces = p.nbuf * p.cpb;
     for (int k0 = 0; k0 < p.N; k0 += KB) {
         __syncthreads();  // the previous pass is done with the tables
-        for (int i = tid; i < p.steps * KB; i += kDirectThreads) {
-            const int j = i / KB, kk = i - j * KB;
-            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;  // fl((k + 1) * w0), fit.py:59
-            double sv, cv;
-            sincos(wk * static_cast<double>(32 * j), &sv, &cv);
-            tab[i] = make_double2(cv, sv);
-        }
-        for (int i = tid; i < KB * 32; i += kDirectThreads) {
-            const int kk = i >> 5, l = i & 31;
-            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
-            double sv, cv;
-            sincos(wk * static_cast<double>(l), &sv, &cv);
-            lane_tab[i] = make_double2(cv, sv);
-        }
+        direct_build_tables(p, k0, KB, tab, lane_tab, tid, THREADS);
         __syncthreads();
-        for (long long b = warp; b < p.nbuf; b += nwarps) {
-            const double* buf = p.x + (b / p.bpc) * p.ld_c + (b % p.bpc) * R;
-            double q[MULTI ? KB : 1], iv[MULTI ? KB : 1];
+        for (long long v = warp; v < npieces; v += nwarps) {
+            long long len;
+            const double* src = direct_piece(p, v, len) + lane;
             double sc[KB], ss[KB];
             double asum = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < KB; ++kk) {
-                sc[kk] = ss[kk] = 0.0;
-                if (MULTI) q[kk] = iv[kk] = 0.0;
-            }
-            for (long long c0 = 0; c0 < R; c0 += 32ll * p.steps) {
-                const long long left = R - c0;
-                const int full = static_cast<int>(left >= 32ll * p.steps ? p.steps : left >> 5);  // steps with all 32 lanes
-                const double* src = buf + c0 + lane;
-                int j = 0;
-                for (; j + 4 <= full; j += 4) {  // four loads in flight per lane
-                    double v[4];
+            for (int kk = 0; kk < KB; ++kk) sc[kk] = ss[kk] = 0.0;
+            const int full = static_cast<int>(len >> 5);  // steps with all 32 lanes
+            int j = 0;
+            for (; j + 4 <= full; j += 4) {  // four loads in flight per lane
+                double x4[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = __ldg(src + 32 * (j + e));
+                for (int e = 0; e < 4; ++e) x4[e] = __ldg(src + 32 * (j + e));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        asum += v[e];
-                        const double2* row = tab + static_cast<size_t>(j + e) * KB;
-#pragma unroll
-                        for (int kk = 0; kk < KB; ++kk) {
-                            const double2 w = row[kk];
-                            sc[kk] = fma(v[e], w.x, sc[kk]);
-                            ss[kk] = fma(v[e], w.y, ss[kk]);
-                        }
-                    }
-                }
-                const int last = static_cast<int>(left >= 32ll * p.steps ? p.steps : (left + 31) >> 5);
-                for (; j < last; ++j) {  // the remaining whole steps and the ragged one
-                    const double v = (c0 + lane + 32ll * j < R) ? __ldg(src + 32 * j) : 0.0;
-                    asum += v;
-                    const double2* row = tab + static_cast<size_t>(j) * KB;
+                for (int e = 0; e < 4; ++e) {
+                    asum += x4[e];
+                    const double2* row = tab + static_cast<size_t>(j + e) * KB;
 #pragma unroll
                     for (int kk = 0; kk < KB; ++kk) {
                         const double2 w = row[kk];
-                        sc[kk] = fma(v, w.x, sc[kk]);
-                        ss[kk] = fma(v, w.y, ss[kk]);
-                    }
-                }
-                // rotate the chunk's sums by w_k (c0 + lane): cos(a + b) = ca cb - sa sb, sin(a + b) = sa cb + ca sb
-#pragma unroll
-                for (int kk = 0; kk < KB; ++kk) {
-                    double ca, sa;
-                    if (!MULTI || c0 == 0) {
-                        const double2 w = lane_tab[kk * 32 + lane];
-                        ca = w.x;
-                        sa = w.y;
-                    } else {
-                        const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
-                        sincos(wk * static_cast<double>(c0 + lane), &sa, &ca);
-                    }
-                    const double qr = ca * sc[kk] - sa * ss[kk];
-                    const double ir = sa * sc[kk] + ca * ss[kk];
-                    if (MULTI) {
-                        q[kk] += qr;
-                        iv[kk] += ir;
-                        sc[kk] = ss[kk] = 0.0;
-                    } else {
-                        sc[kk] = qr;
-                        ss[kk] = ir;
+                        sc[kk] = fma(x4[e], w.x, sc[kk]);
+                        ss[kk] = fma(x4[e], w.y, ss[kk]);
                     }
                 }
             }
+            const int last = static_cast<int>((len + 31) >> 5);
+            for (; j < last; ++j) {  // the remaining whole steps and the ragged one
+                const double xv = (lane + 32ll * j < len) ? __ldg(src + 32 * j) : 0.0;
+                asum += xv;
+                const double2* row = tab + static_cast<size_t>(j) * KB;
+#pragma unroll
+                for (int kk = 0; kk < KB; ++kk) {
+                    const double2 w = row[kk];
+                    sc[kk] = fma(xv, w.x, sc[kk]);
+                    ss[kk] = fma(xv, w.y, ss[kk]);
+                }
+            }
+            // rotate by w_k lane: cos(a + b) = ca cb - sa sb, sin(a + b) = sa cb + ca sb
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) {
-                const double qs = warp_sum(MULTI ? q[kk] : sc[kk]);
-                const double is = warp_sum(MULTI ? iv[kk] : ss[kk]);
-                if (lane == 0 && k0 + kk < p.N) {
-                    p.qi[b * 2 * p.N + k0 + kk] = qs * inv_r;
-                    p.qi[b * 2 * p.N + p.N + k0 + kk] = is * inv_r;
-                }
+                const double2 w = lane_tab[kk * 32 + lane];
+                const double qs = warp_sum(w.x * sc[kk] - w.y * ss[kk]);
+                const double is = warp_sum(w.y * sc[kk] + w.x * ss[kk]);
+                if (lane == 0 && k0 + kk < p.N) direct_store(p, v, k0 + kk, qs, is, inv_r);
             }
             if (k0 == 0) {
                 asum = warp_sum(asum);
-                if (lane == 0) p.dc[b] = asum * inv_r;
+                if (lane == 0) direct_store_sum(p, v, asum, inv_r);
             }
         }
     }
 }
 
-// Two buffers per warp (single-chunk buffers only).  ncu puts the one-buffer kernel at 87 % of the LSU data pipe: a
-// broadcast LDS.128 still writes 512 B of registers per warp, ten of them per step.  A table entry fetched once here
-// serves both buffers, which halves that traffic at twice the accumulators; four steps of both buffers are loaded
-// ahead (with two, the 12 warps per SM the registers allow capped the bytes in flight: 2.4 TB/s).
-// Buffers b and b + 1 of a pair are adjacent in the launch's numbering; an odd last one goes alone.
+// Two pieces per warp.  ncu puts the one-piece kernel at 87 % of the LSU data pipe: a broadcast LDS.128 still writes
+// 512 B of registers per warp, ten of them per step.  A table entry fetched once here serves both pieces, which halves
+// that traffic at twice the accumulators; four steps of both are loaded ahead (with two, the 12 warps per SM the
+// registers allow capped the bytes in flight: 2.4 TB/s).  Pieces v and v + 1 are adjacent in the launch's numbering;
+// an odd last one goes alone.  Same per-lane order of operations as the one-piece kernel: identical numbers.
 template <int KB, int THREADS>
 __global__ void __launch_bounds__(THREADS) demod_direct_pair_kernel(const DirectParams p) {
     extern __shared__ __align__(16) unsigned char direct_smem[];
@@ -1409,74 +1409,62 @@ __global__ void __launch_bounds__(THREADS) demod_direct_pair_kernel(const Direct
     const int tid = threadIdx.x, lane = tid & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * THREADS + tid) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * THREADS) >> 5;
-    const long long R = p.R;
-    const double inv_r = 1.0 / static_cast<double>(R);
-    const long long npairs = (p.nbuf + 1) >> 1;
+    const double inv_r = 1.0 / static_cast<double>(p.R);
+    const long long npieces = p.nbuf * p.cpb;
+    const long long npairs = (npieces + 1) >> 1;
     constexpr int U = 4;
     for (int k0 = 0; k0 < p.N; k0 += KB) {
         __syncthreads();
-        for (int i = tid; i < p.steps * KB; i += THREADS) {
-            const int j = i / KB, kk = i - j * KB;
-            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
-            double sv, cv;
-            sincos(wk * static_cast<double>(32 * j), &sv, &cv);
-            tab[i] = make_double2(cv, sv);
-        }
-        for (int i = tid; i < KB * 32; i += THREADS) {
-            const int kk = i >> 5, l = i & 31;
-            const double wk = static_cast<double>(k0 + kk + 1) * p.w0;
-            double sv, cv;
-            sincos(wk * static_cast<double>(l), &sv, &cv);
-            lane_tab[i] = make_double2(cv, sv);
-        }
+        direct_build_tables(p, k0, KB, tab, lane_tab, tid, THREADS);
         __syncthreads();
         for (long long pr = warp; pr < npairs; pr += nwarps) {
-            const long long b0 = 2 * pr, b1 = (2 * pr + 1 < p.nbuf) ? 2 * pr + 1 : 2 * pr;  // (an odd tail reads itself twice)
-            const double* src0 = p.x + (b0 / p.bpc) * p.ld_c + (b0 % p.bpc) * R + lane;
-            const double* src1 = p.x + (b1 / p.bpc) * p.ld_c + (b1 % p.bpc) * R + lane;
+            const long long v0 = 2 * pr, v1 = (2 * pr + 1 < npieces) ? 2 * pr + 1 : 2 * pr;  // (an odd tail reads itself twice)
+            long long len0, len1;
+            const double* src0 = direct_piece(p, v0, len0) + lane;
+            const double* src1 = direct_piece(p, v1, len1) + lane;
             double sc0[KB], ss0[KB], sc1[KB], ss1[KB];
             double asum0 = 0.0, asum1 = 0.0;
 #pragma unroll
             for (int kk = 0; kk < KB; ++kk) sc0[kk] = ss0[kk] = sc1[kk] = ss1[kk] = 0.0;
-            const int full = static_cast<int>(R >> 5);
+            const long long lmin = len0 < len1 ? len0 : len1, lmax = len0 < len1 ? len1 : len0;
+            const int full = static_cast<int>(lmin >> 5);  // steps whole in both pieces
             int j = 0;
             for (; j + U <= full; j += U) {
-                double v0[U], v1[U];
+                double a[U], b[U];
 #pragma unroll
                 for (int e = 0; e < U; ++e) {
-                    v0[e] = __ldg(src0 + 32 * (j + e));
-                    v1[e] = __ldg(src1 + 32 * (j + e));
+                    a[e] = __ldg(src0 + 32 * (j + e));
+                    b[e] = __ldg(src1 + 32 * (j + e));
                 }
 #pragma unroll
                 for (int e = 0; e < U; ++e) {
-                    asum0 += v0[e];
-                    asum1 += v1[e];
+                    asum0 += a[e];
+                    asum1 += b[e];
                     const double2* row = tab + static_cast<size_t>(j + e) * KB;
 #pragma unroll
                     for (int kk = 0; kk < KB; ++kk) {
                         const double2 w = row[kk];
-                        sc0[kk] = fma(v0[e], w.x, sc0[kk]);
-                        ss0[kk] = fma(v0[e], w.y, ss0[kk]);
-                        sc1[kk] = fma(v1[e], w.x, sc1[kk]);
-                        ss1[kk] = fma(v1[e], w.y, ss1[kk]);
+                        sc0[kk] = fma(a[e], w.x, sc0[kk]);
+                        ss0[kk] = fma(a[e], w.y, ss0[kk]);
+                        sc1[kk] = fma(b[e], w.x, sc1[kk]);
+                        ss1[kk] = fma(b[e], w.y, ss1[kk]);
                     }
                 }
             }
-            const int last = static_cast<int>((R + 31) >> 5);
-            for (; j < last; ++j) {
-                const bool in = lane + 32ll * j < R;
-                const double v0 = in ? __ldg(src0 + 32 * j) : 0.0;
-                const double v1 = in ? __ldg(src1 + 32 * j) : 0.0;
-                asum0 += v0;
-                asum1 += v1;
+            const int last = static_cast<int>((lmax + 31) >> 5);
+            for (; j < last; ++j) {  // remaining steps: whole, ragged, or past the shorter piece's end
+                const double a = (lane + 32ll * j < len0) ? __ldg(src0 + 32 * j) : 0.0;
+                const double b = (lane + 32ll * j < len1) ? __ldg(src1 + 32 * j) : 0.0;
+                asum0 += a;
+                asum1 += b;
                 const double2* row = tab + static_cast<size_t>(j) * KB;
 #pragma unroll
                 for (int kk = 0; kk < KB; ++kk) {
                     const double2 w = row[kk];
-                    sc0[kk] = fma(v0, w.x, sc0[kk]);
-                    ss0[kk] = fma(v0, w.y, ss0[kk]);
-                    sc1[kk] = fma(v1, w.x, sc1[kk]);
-                    ss1[kk] = fma(v1, w.y, ss1[kk]);
+                    sc0[kk] = fma(a, w.x, sc0[kk]);
+                    ss0[kk] = fma(a, w.y, ss0[kk]);
+                    sc1[kk] = fma(b, w.x, sc1[kk]);
+                    ss1[kk] = fma(b, w.y, ss1[kk]);
                 }
             }
 #pragma unroll
@@ -1487,24 +1475,49 @@ __global__ void __launch_bounds__(THREADS) demod_direct_pair_kernel(const Direct
                 const double q1 = warp_sum(w.x * sc1[kk] - w.y * ss1[kk]);
                 const double i1 = warp_sum(w.y * sc1[kk] + w.x * ss1[kk]);
                 if (lane == 0 && k0 + kk < p.N) {
-                    p.qi[b0 * 2 * p.N + k0 + kk] = q0 * inv_r;
-                    p.qi[b0 * 2 * p.N + p.N + k0 + kk] = i0 * inv_r;
-                    if (b1 != b0) {
-                        p.qi[b1 * 2 * p.N + k0 + kk] = q1 * inv_r;
-                        p.qi[b1 * 2 * p.N + p.N + k0 + kk] = i1 * inv_r;
-                    }
+                    direct_store(p, v0, k0 + kk, q0, i0, inv_r);
+                    if (v1 != v0) direct_store(p, v1, k0 + kk, q1, i1, inv_r);
                 }
             }
             if (k0 == 0) {
                 asum0 = warp_sum(asum0);
                 asum1 = warp_sum(asum1);
                 if (lane == 0) {
-                    p.dc[b0] = asum0 * inv_r;
-                    if (b1 != b0) p.dc[b1] = asum1 * inv_r;
+                    direct_store_sum(p, v0, asum0, inv_r);
+                    if (v1 != v0) direct_store_sum(p, v1, asum1, inv_r);
                 }
             }
         }
     }
+}
+
+// Chunked buffers: harmonic k of buffer b is sum_c exp(i w_k c0_c) S_c with S_c the chunk's sums taken from its own
+// start c0_c = c * 32 * steps -- one thread per (buffer, harmonic), the chunks in order; thread k = N sums the means.
+__global__ void direct_combine_kernel(const DirectParams p) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const int per = p.N + 1;
+    if (i >= p.nbuf * per) return;
+    const long long b = i / per;
+    const int k = static_cast<int>(i - b * per);
+    const double inv_r = 1.0 / static_cast<double>(p.R);
+    const double* part = p.part + b * p.cpb * (2 * p.N + 1);
+    if (k == p.N) {
+        double s = 0.0;
+        for (long long c = 0; c < p.cpb; ++c) s += part[c * (2 * p.N + 1) + 2 * p.N];
+        p.dc[b] = s * inv_r;
+        return;
+    }
+    const double wk = static_cast<double>(k + 1) * p.w0;
+    double q = 0.0, iv = 0.0;
+    for (long long c = 0; c < p.cpb; ++c) {
+        double sa, ca;
+        sincos(wk * static_cast<double>(c * 32ll * p.steps), &sa, &ca);
+        const double qc = part[c * (2 * p.N + 1) + k], ic = part[c * (2 * p.N + 1) + p.N + k];
+        q += ca * qc - sa * ic;
+        iv += sa * qc + ca * ic;
+    }
+    p.qi[b * 2 * p.N + k] = q * inv_r;
+    p.qi[b * 2 * p.N + p.N + k] = iv * inv_r;
 }
 
 }  // namespace dfk

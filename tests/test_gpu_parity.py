@@ -733,15 +733,16 @@ def test_direct_lockin_shapes(torch_mod, ctx, R, nh, f_mod):
     assert worst <= IQ_TOL, worst
 
 
-@pytest.mark.parametrize("R,nh", [(517, 10), (4000, 7), (64, 9)])
+@pytest.mark.parametrize("R,nh", [(517, 10), (4000, 7), (64, 9), (40001, 10)])
 def test_direct_lockin_pairs(torch_mod, ctx, R, nh):
-    """With enough buffers the table-driven lock-in takes two per warp: same numbers as one per warp (the per-lane
-    order of operations is the same), an odd last buffer included, and the oracle's on a sample of them."""
+    """With enough pieces the table-driven lock-in takes two per warp: same numbers as one per warp (the per-lane
+    order of operations is the same), an odd last one included, and the oracle's on a sample of the buffers.  40 001
+    samples: three chunks per buffer, the last one ragged, so that pairs straddle buffers and lengths."""
     from deepfmkit_b200 import _lib
     f_samp, f_mod = 200e3, 1234.5
     w0 = orc.rad_per_sample(f_samp, f_mod)
     assert _lib.demod_path(R, w0) == 0
-    nbuf = 2 * 12 * 160 + 1
+    nbuf = 2 * 12 * 160 + 1 if R < 10000 else 1281
     rng = np.random.RandomState(R)
     t = np.arange(nbuf * R)
     x = 1.0 + np.cos(0.4 + 5.0 * np.cos(w0 * t + 0.3)) + 0.01 * rng.randn(nbuf * R)
