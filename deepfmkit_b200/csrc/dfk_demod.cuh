@@ -4,7 +4,7 @@
 //   Q_k = mean(x[t] * cos(fl((k)*w0)*t)),  I_k = mean(x[t] * sin(fl(k*w0)*t)),  k = 1..N,  dc = mean(x),
 // with t restarting at 0 in every buffer.
 //
-// Four kernels, chosen by the launcher in dfk_b200.cu from the geometry (dfk_demod_plan.h):
+// The kernels, chosen by the launcher in dfk_b200.cu from the geometry (dfk_demod_plan.h):
 //
 // demod_fold_kernel   -- long fold lengths (P > 256, e.g. 1 MHz / 1 kHz).  Needs a whole even number P of samples
 //   that holds whole modulation periods, and whole folds per buffer.  A persistent CTA streams its buffers from
@@ -16,11 +16,14 @@
 //   buffers from the TMA stage to the outputs, harmonics by a product with a twiddle table in shared memory.
 // demod_period_kernel -- one period per buffer (R = P, P % 4 == 0): the tile scheme with quarter-wave symmetry and
 //   a 2 x 4 register tile per lane, because at this shape the product, not HBM, is the bound.
-// demod_direct_kernel -- anything else (incommensurate period, unaligned pointer, strided channels): one CTA per
-//   buffer, harmonics in blocks of kDirectKB with a per-thread rotation recurrence re-synchronised with sincos
-//   every kDirectResync steps.  Compute-bound; later harmonic blocks re-read the buffer from L1/L2.
+// demod_fold_long_kernel -- fold lengths beyond 2048 samples in column chunks; in STORE mode the folded period of an
+//   interleaved (time-major) multi-channel buffer for project_interleaved_kernel.
+// demod_direct_kernel / demod_direct_pair_kernel -- anything else (incommensurate period, unaligned pointer, strided
+//   channels): a warp per buffer (or 16 384-sample chunk of a long one; two per warp when there are enough), cos/sin
+//   of the lane-independent part of the angle from a shared-memory table, two FMAs per sample and harmonic; 8 to 16
+//   harmonics per pass, further passes re-read the record; direct_combine_kernel adds the chunks up.
 //
-// In the three TMA kernels every sample is read from HBM exactly once: 8 B/sample + 8(2N+1) B/buffer written.
+// In the TMA kernels every sample is read from HBM exactly once: 8 B/sample + 8(2N+1) B/buffer written.
 #pragma once
 #include "dfk_common.cuh"
 #include "dfk_demod_plan.h"
