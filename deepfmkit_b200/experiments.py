@@ -144,6 +144,31 @@ class Experiment:
                                           if k in self._expected_params_keys or k.startswith("_exp_")}
                 counter += self.n_trials if first_trial_only else 1
 
+    def _assemble_results(self, parts, grid_shape, ntr):
+        """The result dictionary from the per-rank tables ``{analysis: (stats[points, cols, 6], values[points, trials,
+        cols])}``, ranks in order, each holding a contiguous range of grid points (one part on one GPU)."""
+        npoints_all = int(np.prod(grid_shape)) if grid_shape else 1
+        results: Dict[str, Any] = {"axes": self.axes}
+        for a in self.analyses:
+            st = np.concatenate([p[a["name"]][0] for p in parts], axis=0)
+            allv = np.concatenate([p[a["name"]][1] for p in parts], axis=0).reshape(grid_shape + (ntr, len(RESULT_KEYS)))
+            if st.shape[0] != npoints_all:
+                raise RuntimeError(f"gathered {st.shape[0]} grid points, expected {npoints_all}")
+            cols = a.get("result_cols") or sorted(RESULT_KEYS)
+            out = {}
+            for col in cols:
+                if col not in RESULT_KEYS:
+                    grid = np.full(grid_shape + (ntr,), np.nan)
+                    out[col] = {"all_trials": grid, **{k: np.full(grid_shape, np.nan) for k in ("mean", "std", "min", "max", "worst")}}
+                    continue
+                c = RESULT_KEYS.index(col)
+                d = {"all_trials": np.ascontiguousarray(allv[..., c])}
+                for k, name in enumerate(("mean", "std", "min", "max", "worst")):
+                    d[name] = st[:, c, k].reshape(grid_shape) if grid_shape else st[0, c, k]
+                out[col] = d
+            results[a["name"]] = out
+        return results
+
     def run(self, n_cores: Optional[int] = None, filename: Optional[str] = None, device: Optional[int] = None,
             max_resident_bytes: int = 8 << 30, group=None) -> Dict[str, Any]:
         import torch
@@ -269,24 +294,7 @@ class Experiment:
             torch.distributed.all_gather_object(parts, local, group=group)
         else:
             parts = [local]
-        results: Dict[str, Any] = {"axes": self.axes}
-        for a in self.analyses:
-            st = np.concatenate([p[a["name"]][0] for p in parts], axis=0)
-            allv = np.concatenate([p[a["name"]][1] for p in parts], axis=0).reshape(grid_shape + (ntr, len(RESULT_KEYS)))
-            assert st.shape[0] == npoints_all
-            cols = a.get("result_cols") or sorted(RESULT_KEYS)
-            out = {}
-            for col in cols:
-                if col not in RESULT_KEYS:
-                    grid = np.full(grid_shape + (ntr,), np.nan)
-                    out[col] = {"all_trials": grid, **{k: np.full(grid_shape, np.nan) for k in ("mean", "std", "min", "max", "worst")}}
-                    continue
-                c = RESULT_KEYS.index(col)
-                d = {"all_trials": np.ascontiguousarray(allv[..., c])}
-                for k, name in enumerate(("mean", "std", "min", "max", "worst")):
-                    d[name] = st[:, c, k].reshape(grid_shape) if grid_shape else st[0, c, k]
-                out[col] = d
-            results[a["name"]] = out
+        results = self._assemble_results(parts, grid_shape, ntr)
         self.results = results
         if filename is not None:
             self.save_results(filename)

@@ -183,6 +183,57 @@ def test_sharded_gather_world_size_2_gloo(tmp_path):
     assert "GLOO_OK" in out.stdout
 
 
+_GLOO_EXPERIMENT_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+from deepfmkit_b200 import Experiment
+from deepfmkit_b200.experiments import RESULT_KEYS
+from deepfmkit_b200.sharding import slab_bounds
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+exp = Experiment("gloo")
+exp.add_axis("a", np.arange(3.0)); exp.add_axis("b", np.arange(5.0))
+exp.add_analysis("nls", "nls"); exp.add_analysis("ekf", "ekf", result_cols=["m", "nope"])
+grid_shape, ntr, npoints = (3, 5), 4, 15
+lo, hi = slab_bounds(npoints, world, rank)
+# stand-in for the per-rank simulate + fit + statistics: every entry encodes (point, trial, column, statistic)
+pts = np.arange(lo, hi)
+local = {{}}
+for name, off in (("nls", 0.0), ("ekf", 0.5)):
+    st = off + pts[:, None, None] * 100 + np.arange(len(RESULT_KEYS))[None, :, None] * 10 + np.arange(6)[None, None, :]
+    v = off + pts[:, None, None] * 100 + np.arange(ntr)[None, :, None] * 10 + np.arange(len(RESULT_KEYS))[None, None, :]
+    local[name] = (st.astype(float), v.astype(float))
+parts = [None] * world
+dist.all_gather_object(parts, local)
+res = exp._assemble_results(parts, grid_shape, ntr)
+c = RESULT_KEYS.index("m")
+point = np.arange(npoints).reshape(grid_shape)
+assert np.array_equal(res["nls"]["m"]["mean"], point * 100 + c * 10 + 0)
+assert np.array_equal(res["nls"]["m"]["worst"], point * 100 + c * 10 + 4)
+assert np.array_equal(res["ekf"]["m"]["all_trials"], 0.5 + point[..., None] * 100 + np.arange(ntr) * 10 + c)
+assert np.all(np.isnan(res["ekf"]["nope"]["mean"])) and res["ekf"]["nope"]["all_trials"].shape == (3, 5, 4)
+assert sorted(res["nls"]) == sorted(RESULT_KEYS) and sorted(res["ekf"]) == ["m", "nope"]
+if rank == 0:
+    print("GLOO_EXPERIMENT_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_experiment_assembly_world_size_2_gloo(tmp_path):
+    """Experiment.run(group=...): grid points in contiguous ranges per rank, per-rank tables gathered as objects and
+    assembled in rank order -- the host side of it, with stand-in tables, over a 2-rank gloo group."""
+    script = tmp_path / "worker_exp.py"
+    script.write_text(_GLOO_EXPERIMENT_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "GLOO_EXPERIMENT_OK" in out.stdout
+
+
 def test_bench_reference_arm_contract():
     """bench.py's CPU arm: the port's pool schedule agrees with the sequential oracle, and the arm that times the
     reference itself (baseline/_ref, when installed) returns the same rows as the port on the same sample."""
