@@ -102,12 +102,16 @@ struct LpsdParams {
     double* group_sum;      // [C][ngroups]
 };
 
+// 1 / k^2, k = 1..64: the series below spends its time in this factor (a division per term was ~90 % of the LPSD
+// kernel: the window is evaluated once per sample and group of segments, 40-50 terms each at 200 dB side lobes)
+__device__ __constant__ double kInvSquare[64] = {1.0 / 1.0, 1.0 / 4.0, 1.0 / 9.0, 1.0 / 16.0, 1.0 / 25.0, 1.0 / 36.0, 1.0 / 49.0, 1.0 / 64.0, 1.0 / 81.0, 1.0 / 100.0, 1.0 / 121.0, 1.0 / 144.0, 1.0 / 169.0, 1.0 / 196.0, 1.0 / 225.0, 1.0 / 256.0, 1.0 / 289.0, 1.0 / 324.0, 1.0 / 361.0, 1.0 / 400.0, 1.0 / 441.0, 1.0 / 484.0, 1.0 / 529.0, 1.0 / 576.0, 1.0 / 625.0, 1.0 / 676.0, 1.0 / 729.0, 1.0 / 784.0, 1.0 / 841.0, 1.0 / 900.0, 1.0 / 961.0, 1.0 / 1024.0, 1.0 / 1089.0, 1.0 / 1156.0, 1.0 / 1225.0, 1.0 / 1296.0, 1.0 / 1369.0, 1.0 / 1444.0, 1.0 / 1521.0, 1.0 / 1600.0, 1.0 / 1681.0, 1.0 / 1764.0, 1.0 / 1849.0, 1.0 / 1936.0, 1.0 / 2025.0, 1.0 / 2116.0, 1.0 / 2209.0, 1.0 / 2304.0, 1.0 / 2401.0, 1.0 / 2500.0, 1.0 / 2601.0, 1.0 / 2704.0, 1.0 / 2809.0, 1.0 / 2916.0, 1.0 / 3025.0, 1.0 / 3136.0, 1.0 / 3249.0, 1.0 / 3364.0, 1.0 / 3481.0, 1.0 / 3600.0, 1.0 / 3721.0, 1.0 / 3844.0, 1.0 / 3969.0, 1.0 / 4096.0};
+
 DFK_D double bessel_i0(double x) {
     // power series sum (x^2/4)^k / (k!)^2: all terms positive, converges in < 60 terms for x <= 40
     const double q = 0.25 * x * x;
     double term = 1.0, sum = 1.0;
     for (int k = 1; k < 200; ++k) {
-        term *= q / (static_cast<double>(k) * static_cast<double>(k));
+        term *= k <= 64 ? q * kInvSquare[k - 1] : q / (static_cast<double>(k) * static_cast<double>(k));
         sum += term;
         if (term < 1e-17 * sum) break;
     }
