@@ -145,6 +145,20 @@ def test_slab_bounds_cover_and_balance():
         slab_bounds(10, 2, 2)
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/dfk_b200.h must compile as C99 with no C++ or CUDA types in it, and
+    carry the ABI version the binding expects."""
+    from deepfmkit_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('#include "dfk_b200.h"\n'
+                   f'int main(void) {{ return DFK_ABI_VERSION == {_lib.ABI_VERSION} && DFK_ASD_TRIAL_DOUBLES == '
+                   f'{_lib.ASD_TRIAL_DOUBLES} ? 0 : 1; }}\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0
+
+
 _GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
