@@ -145,6 +145,29 @@ def test_slab_bounds_cover_and_balance():
         slab_bounds(10, 2, 2)
 
 
+def test_dev_overrides_are_explicit_and_validated(lib):
+    """Tuning overrides exist only through dfk_dev_set (the library never reads the environment); names are bounded,
+    the staged-copy geometry is range-checked, and dfk_dev_clear restores the defaults.  Host calls only."""
+    assert lib.dfk_dev_set(b"DFK_NO_TILE", 1) == 0
+    assert lib.dfk_dev_set(b"X" * 40, 1) != 0 and b"override name" in lib.dfk_last_error()
+    assert lib.dfk_dev_set(b"", 1) != 0
+    for name, good, bad in ((b"DFK_STAGE_KB", 4096, 16), (b"DFK_STAGE_KB", 65536, 65537 * 2), (b"DFK_STAGERS", 6, 1),
+                            (b"DFK_STAGERS", 8, 9)):
+        assert lib.dfk_dev_set(name, good) == 0, name
+        assert lib.dfk_dev_set(name, bad) != 0, (name, bad)
+    assert lib.dfk_dev_set(b"DFK_COPY_THREADS", 0) == 0 and lib.dfk_dev_set(b"DFK_COPY_NT", 1) == 0
+    for i in range(40):  # the table of kernel overrides is finite and says so
+        rc = lib.dfk_dev_set(f"DFK_TEST_{i}".encode(), i)
+        if rc != 0:
+            assert b"table full" in lib.dfk_last_error()
+            break
+    else:
+        raise AssertionError("override table never filled")
+    lib.dfk_dev_clear()
+    assert lib.dfk_dev_set(b"DFK_NO_TILE", 0) == 0
+    lib.dfk_dev_clear()
+
+
 def test_header_is_plain_c(tmp_path):
     """The drop-in boundary is a C ABI: include/dfk_b200.h must compile as C99 with no C++ or CUDA types in it, and
     carry the ABI version the binding expects."""
